@@ -1,0 +1,95 @@
+"""GPU probe: correctness of the tcgen05 GEMM on the shapes of Appendix B + a CUDA-event throughput sweep."""
+import sys, os, json, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import lrce_b200
+from lrce_b200 import ops
+
+torch.manual_seed(0)
+dev = "cuda"
+
+
+def ref(a, w, bias, epi, res, ln):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if epi == ops.EPI_BIAS_GELU:
+        y = torch.nn.functional.gelu(y)
+    if epi == ops.EPI_BIAS_RESIDUAL:
+        y = y + res.float()
+    if epi == ops.EPI_BIAS_LN:
+        y = torch.nn.functional.layer_norm(y, (y.shape[1],), ln[0], ln[1], ln[2])
+    return y
+
+
+def check(M, N, K, epi, fp32=False):
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev).bfloat16() if epi == ops.EPI_BIAS_RESIDUAL else None
+    ln = (torch.rand(N, device=dev) + 0.5, torch.randn(N, device=dev), 1e-5) if epi == ops.EPI_BIAS_LN else None
+    y = ops.gemm(a, w, bias, epilogue=epi, residual=res, out_fp32=fp32, ln=ln)
+    torch.cuda.synchronize()
+    r = ref(a, w, bias, epi, res, ln)
+    err = (y.float() - r).abs().max().item()
+    rel = ((y.float() - r).norm() / r.norm()).item()
+    ok = rel < (1e-5 if fp32 else 6e-3)
+    print(f"M={M:7d} N={N:5d} K={K:5d} epi={epi} fp32={int(fp32)} max_abs={err:.4e} rel_l2={rel:.3e} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def bench(M, N, K, epi, iters=20):
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev).bfloat16() if epi == ops.EPI_BIAS_RESIDUAL else None
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, bias, epilogue=epi, residual=res, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.gemm(a, w, bias, epilogue=epi, residual=res, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * M * N * K / ms / 1e9
+    # cuBLAS comparison (library baseline)
+    for _ in range(3):
+        torch.matmul(a, w.t())
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, w.t())
+    e1.record(); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / iters
+    print(f"BENCH M={M} N={N} K={K} epi={epi}: {ms*1e3:.1f} us  {tf:.1f} TFLOP/s  (cuBLAS matmul {ms2*1e3:.1f} us {2.0*M*N*K/ms2/1e9:.1f} TF)", flush=True)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), flush=True)
+    ok = True
+    ok &= check(128, 128, 64, ops.EPI_BIAS, fp32=True)
+    ok &= check(128, 128, 128, ops.EPI_BIAS, fp32=True)
+    ok &= check(256, 256, 256, ops.EPI_BIAS, fp32=True)
+    ok &= check(300, 384, 128, ops.EPI_BIAS)
+    ok &= check(882, 3072, 1024, ops.EPI_BIAS)
+    ok &= check(3528, 2048, 512, ops.EPI_BIAS_GELU)
+    ok &= check(3528, 512, 2048, ops.EPI_BIAS_RESIDUAL)
+    ok &= check(14112, 768, 256, ops.EPI_BIAS)
+    ok &= check(56448, 128, 96, ops.EPI_BIAS_LN)
+    ok &= check(1000, 128, 96, ops.EPI_BIAS_LN)
+    ok &= check(14112, 256, 512, ops.EPI_BIAS)
+    ok &= check(32, 768, 768, ops.EPI_BIAS, fp32=True)
+    ok &= check(160, 1024, 768, ops.EPI_BIAS, fp32=True)
+    print("ALL_OK" if ok else "SOME_FAIL", flush=True)
+    if ok or "--force-bench" in sys.argv:
+        bench(8192, 8192, 8192, ops.EPI_BIAS)
+        bench(56448, 1536, 512, ops.EPI_BIAS)
+        bench(56448, 2048, 512, ops.EPI_BIAS_GELU)
+        bench(56448, 512, 2048, ops.EPI_BIAS_RESIDUAL)
+        bench(56448, 512, 512, ops.EPI_BIAS_RESIDUAL)
+        bench(903168, 384, 128, ops.EPI_BIAS)
+        bench(903168, 512, 128, ops.EPI_BIAS_GELU)
+        bench(903168, 128, 512, ops.EPI_BIAS_RESIDUAL)
+        bench(14112, 4096, 1024, ops.EPI_BIAS_GELU)
+        bench(15456, 18432, 768, ops.EPI_BIAS)

@@ -1,0 +1,113 @@
+// host_common.cu — error convention, arch gate and TMA descriptor encoding for liblrce_b200.so.
+#include "host_common.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace lrce {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* last_error() { return g_err; }
+
+int require_sm100() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_rc = LRCE_EARCH;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice failed: %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
+  if (dev == cached_dev) return cached_rc;
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cached_dev = dev;
+  if (major != 10) {
+    set_error("liblrce_b200 requires an sm_100a (B200) device, found compute capability %d.%d; no fallback exists",
+              major, minor);
+    cached_rc = LRCE_EARCH;
+  } else {
+    cached_rc = LRCE_OK;
+  }
+  return cached_rc;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
+  return LRCE_OK;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available from the driver");
+    return LRCE_EDRIVER;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * 2) & 15) != 0) {
+    set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (base=%p, ld=%llu elems)", base,
+              (unsigned long long)ld_elems);
+    return LRCE_EINVAL;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_inner, box_outer);
+    return LRCE_EDRIVER;
+  }
+  return LRCE_OK;
+}
+
+}  // namespace lrce
+
+extern "C" const char* lrce_last_error(void) { return lrce::last_error(); }
+extern "C" int lrce_abi_version(void) { return LRCE_ABI_VERSION; }

@@ -1,0 +1,33 @@
+// host_common.h — host-side helpers private to liblrce_b200.so: error convention, arch gate, TMA descriptor encode.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lrce_b200.h"
+
+namespace lrce {
+
+// thread-local last-error message (retrieved through lrce_last_error())
+void set_error(const char* fmt, ...);
+// returns LRCE_OK only on a compute-capability 10.x device; there is no fallback path.
+int require_sm100();
+// cudaGetLastError() -> LRCE_ECUDA + message
+int check_launch(const char* what);
+
+// 2-D bf16 tensor map with 128-byte swizzle: global tensor [outer][inner] with row pitch ld_elems,
+// box = box_outer x box_inner (box_inner * 2 B must be 128 B for the UMMA SW128 K-major layout).
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                      uint32_t box_inner, uint32_t box_outer);
+
+int sm_count();
+
+}  // namespace lrce
+
+#define LRCE_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::lrce::set_error(__VA_ARGS__);    \
+      return LRCE_EINVAL;                \
+    }                                    \
+  } while (0)

@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — LRCE forward throughput on B200 (BASELINE.json metric: clips/sec of the E2E forward).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path (default workload: configs[1])
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                      # clip-sharded, weak scaling, NCCL logit gather
+    python bench.py --impl reference --steps 2 --warmup 1           # CPU baseline arm (oracle port of the reference)
+
+A "step" is one E2E forward over one batch of `--batch` synthetic clips per GPU (default 32 = configs[1]: MSVD-QA
+open-ended eval forward, batch 32 bf16, temporal-scale 3). One JSON line is printed by rank 0.
+  value  : clips/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e    : clips/s through the public module call with HOST (pinned) inputs: H2D of the clips/ids and D2H of the logits
+           are inside the timed region
+  roofline : the dominant kernel family (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of its launches inside
+           the timed region, against the measured sustained bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (a torch restatement of the reference pinned to its golden vectors) timed on this
+           box's host cores on a bounded sample (rank 0, N=1 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {  # reference configs/*.json
+    "msvd-qa-oe": dict(kind="oe", num_classes=1000, text_seq_len=32),
+    "msrvtt-qa-oe": dict(kind="oe", num_classes=1500, text_seq_len=37),
+    "tgif-frameqa": dict(kind="oe", num_classes=1000, text_seq_len=30),
+    "tgif-action": dict(kind="mc", num_classes=1, text_seq_len=40),
+    "tgif-transition": dict(kind="mc", num_classes=1, text_seq_len=40),
+    "tgif-count": dict(kind="count", num_classes=1, text_seq_len=30),
+}
+GFLOP_PER_CLIP = 303.96  # Swin-B 3 x 96.354 + canonical encoder 14.90 (msvd-qa-oe)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["source"] = "fallback"
+    return d
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def model_kwargs(cfg):
+    return dict(feature_dim=768, num_classes=cfg["num_classes"], video_feature_res=[7, 7], video_feature_dim=1024,
+                frame_sample_size=5, temporal_scale=[3], text_seq_len=cfg["text_seq_len"])
+
+
+def synth_inputs(batch, cfg, seed):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    L = cfg["text_seq_len"]
+    lead = (batch, 5) if cfg["kind"] == "mc" else (batch,)
+    clips = torch.rand((batch, 3, 5, 3, 224, 224), generator=g)
+    ids = torch.randint(1000, 30522, lead + (L,), generator=g)
+    ids[..., 0] = 101
+    ids[..., 19] = 102
+    ids[..., 20:] = 0
+    mask = torch.zeros(lead + (L,), dtype=torch.int64)
+    mask[..., :20] = 1
+    types = torch.zeros(lead + (L,), dtype=torch.int64)
+    return clips, ids, mask, types
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(cfg_name, max_seconds=25.0, batch=2):
+    """times the CPU oracle (port of the reference's fp32 CPU path) on all host cores; bounded sample."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lrce_oracle as O
+    import weights as W
+
+    cfg = CONFIGS[cfg_name]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = W.make_e2e_state_dict(cfg["num_classes"], cfg["text_seq_len"], 3, seed=0)
+    clips, ids, mask, types = W.make_inputs(batch, 3, cfg["text_seq_len"], seed=1, n_candidates=5 if cfg["kind"] == "mc" else 0)
+    times = []
+    t_start = time.time()
+    with torch.no_grad():
+        O.e2e_forward(sd, clips, ids, mask, types, cfg["kind"])  # warm-up
+        while len(times) < 5 and (time.time() - t_start) < max_seconds:
+            t0 = time.time()
+            O.e2e_forward(sd, clips, ids, mask, types, cfg["kind"])
+            times.append(time.time() - t0)
+    best = min(times)
+    return {"value": batch / best, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{cfg_name} E2E forward, batch {batch} fp32, best of {len(times)} after 1 warm-up "
+                      f"(oracle/lrce_oracle.py on torch CPU, {cores} threads)"}, best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, best = cpu_baseline(args.config, max_seconds=max(20.0, 12.0 * (args.steps + args.warmup)), batch=2)
+    line = {"impl": "reference", "metric": "clips/sec LRCE fwd", "value": base["value"], "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config} E2E eval forward (CPU, batch 2 sample of the batch-{args.batch} workload)"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import lrce_b200
+    from lrce_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200): the LRCE hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    cfg = CONFIGS[args.config]
+    cls = {"oe": lrce_b200.E2EOpenEnded, "mc": lrce_b200.E2EMultipleChoice, "count": lrce_b200.E2ECount}[cfg["kind"]]
+    torch.manual_seed(0)
+    model = cls(pretrained=False, **model_kwargs(cfg)).to(dev).eval()
+    B = args.batch
+    host = [t.pin_memory() for t in synth_inputs(B, cfg, seed=1 + rank)]
+    devin = [t.to(dev) for t in host]
+    n_out = (B, 5) if cfg["kind"] == "mc" else ((B,) if cfg["kind"] == "count" else (B, cfg["num_classes"]))
+    gathered = torch.empty((world,) + n_out, device=dev) if world > 1 else None
+    host_out = torch.empty(n_out, dtype=torch.float32).pin_memory()
+
+    def step(inputs):
+        with torch.no_grad():
+            y = model(*inputs)
+            if world > 1:  # clip-sharded eval: the only collective is the final logit gather
+                dist.all_gather_into_tensor(gathered, y)
+            return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(devin)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, per-kernel event trace on
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.trace = []
+    launches0 = ops.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(devin)
+    e1.record()
+    barrier()
+    trace, ops.trace = ops.trace, None
+    gpu_launches = ops.launches - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- timed region 2: end to end through the public module call with host buffers
+    for _ in range(2):
+        step([t.to(dev, non_blocking=True) for t in host])
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        y = step([t.to(dev, non_blocking=True) for t in host])
+        host_out.copy_(y, non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peaks = load_peaks()
+        fam = {}
+        for name, tag, flops, nbytes, a, b in trace:
+            d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+            d["launches"] += 1
+        kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                       "tflops": v["flops"] / v["ms"] / 1e9 if v["ms"] else 0.0,
+                       "gbs": v["bytes"] / v["ms"] / 1e6 if v["ms"] else 0.0} for k, v in fam.items()}
+        g = fam.get("lrce_gemm_bf16", {"ms": 1.0, "flops": 0.0, "launches": 1})
+        achieved = g["flops"] / g["ms"] / 1e9
+        peak = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+        clips_per_s = world * B * args.steps / (ms / 1e3)
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        line = {
+            "metric": "clips/sec LRCE fwd", "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.config} E2E eval forward (Video Swin-B + BERT-base + recurrent encoder + head), "
+                                   f"batch {B} clips/GPU, temporal-scale 3, random-init weights",
+                       "global_batch": world * B, "parallelism": f"clip-sharded dp{world}" + (" + NCCL logit all_gather" if world > 1 else ""),
+                       "l2_policy": "inputs (289 MB of fp32 clips per step) and every stage tensor exceed the 126 MB L2"},
+            "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": host_out.numel() * 4},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all Linear layers)", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": f"{peaks['source']} bf16_tflops_sustained", "traffic": None,
+                         "launches_per_step": g["launches"] / args.steps, "share_of_step": g["ms"] / ms,
+                         "whole_forward_tflops": clips_per_s / world * GFLOP_PER_CLIP / 1e3,
+                         "whole_forward_frac": clips_per_s / world * GFLOP_PER_CLIP / 1e3 / peak},
+            "kernels": kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline(args.config, max_seconds=25.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="msvd-qa-oe", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)

@@ -1,7 +1,7 @@
 """ctypes binding of liblrce_b200.so (the C ABI declared in include/lrce_b200.h).
 
 There is deliberately no fallback: if the shared library has not been built (``python -c "import __graft_entry__ as g;
-g.build()"`` or ``make -C vqa-lrce-kbs-2023_b200/csrc``) loading raises, and every entry point raises RuntimeError on a
+g.build()"`` or ``make -C vqa-lrce-kbs-2023_b200/csrc``) loading raises, and every entry point raises LrceError on a
 non-zero return code with the library's own message.
 """
 import ctypes
@@ -11,13 +11,25 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblrce_b200.so")
 
 _c = ctypes
-_vp, _i, _f = _c.c_void_p, _c.c_int, _c.c_float
+_vp, _i, _f, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGNATURES = {
     "lrce_abi_version": [],
     "lrce_last_error": [],
     "lrce_gemm_bf16": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _vp],
+    "lrce_layernorm_bf16": [_vp, _vp, _vp, _vp, _f, _ll, _i, _i, _vp],
+    "lrce_patch_merge_ln_bf16": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp],
+    "lrce_patch_gather_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "lrce_window_remap_bf16": [_vp, _vp] + [_i] * 12 + [_vp],
+    "lrce_remap_index": [_vp, _vp, _vp] + [_i] * 9 + [_vp],
+    "lrce_window_bias_pack": [_vp, _vp, _i, _vp],
+    "lrce_window_attention_bf16": [_vp, _vp, _vp] + [_i] * 8 + [_vp],
+    "lrce_video_posembed_ln": [_vp] * 7 + [_f, _vp, _i, _i, _i, _i, _vp],
+    "lrce_text_posembed_ln": [_vp, _i] + [_vp] * 4 + [_f, _vp, _i, _i, _vp],
+    "lrce_skinny_linear": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "lrce_cross_attention": [_vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
+    "lrce_recurrent_update": [_vp] * 7 + [_f, _vp, _i, _vp],
 }
 _RESTYPES = {"lrce_last_error": _c.c_char_p}
 

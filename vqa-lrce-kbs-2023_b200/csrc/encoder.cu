@@ -1,0 +1,405 @@
+// encoder.cu — the recurrent cross-modal encoder's small kernels (lrce/models/fusionv3.py, embedding.py).
+//
+// The heavy part of the encoder — the K/V in-projection of every memory token for all 12 layers — is one tcgen05 GEMM
+// (gemm_tc.cu). What remains is the single summarisation token walking 12 layers x S segments (fusionv3.py:41-51):
+// a chain of (rows <= 32) x 768 mat-vec-like products that is weight-bandwidth / latency bound. Kernels here:
+//   video_posembed_ln / text_posembed_ln : embedding.py:47-63 / :17-23 fused (CLS row, 3 adds, LayerNorm eps 1e-12)
+//   skinny_linear   : Y = act(LN?(Xa + Xb) W^T + b) for <= 32 rows per CTA-row; weights streamed once with 16-byte
+//                     loads straight into mma.sync B fragments (K order permuted consistently on both operands),
+//                     K split across the 8 warps of a CTA, the residual-add + LayerNorm of the PREVIOUS sub-layer
+//                     fused as prologue (post-norm decoder: x = LN(x + f(x)))
+//   cross_attention : one warp per (row, head): 1 query x (150 video + Lt text) keys of the precomputed K/V
+//   recurrent_update: tok = LN_f(tok + LN3(h + y))  (fusionv3.py:47-48 after the 12th layer)
+#include "host_common.h"
+#include "lrce_common.cuh"
+
+namespace lrce {
+
+constexpr int ENC_D = 768;
+
+// ---------------------------------------------------------------------------------------------------------------
+// row helpers: one warp owns a 768-wide row, lane holds 24 values as 3 chunks of 8 at columns (i*32 + lane)*8
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void row768_ln_store(float (&v)[24], const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float eps, int lane,
+                                                bf16* out_bf16, float* out_f32) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / ENC_D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const float d = v[i] - mean; ss += d * d; }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / ENC_D) + eps);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[c * 8 + j] - mean) * rstd * __ldg(gamma + col + j) + __ldg(beta + col + j);
+    if (out_bf16) {
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(out_bf16 + col) = u;
+    }
+    if (out_f32) {
+      *reinterpret_cast<float4*>(out_f32 + col) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(out_f32 + col + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[c * 8 + j] = o[j];
+  }
+}
+
+__device__ __forceinline__ void row768_add_f32(float (&v)[24], const float* __restrict__ src, int lane) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + col + 4));
+    v[c * 8 + 0] += a.x; v[c * 8 + 1] += a.y; v[c * 8 + 2] += a.z; v[c * 8 + 3] += a.w;
+    v[c * 8 + 4] += b.x; v[c * 8 + 5] += b.y; v[c * 8 + 6] += b.z; v[c * 8 + 7] += b.w;
+  }
+}
+__device__ __forceinline__ void row768_add_bf16(float (&v)[24], const bf16* __restrict__ src, int lane) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + col));
+    float2 f;
+    f = unpack_bf16x2(u.x); v[c * 8 + 0] += f.x; v[c * 8 + 1] += f.y;
+    f = unpack_bf16x2(u.y); v[c * 8 + 2] += f.x; v[c * 8 + 3] += f.y;
+    f = unpack_bf16x2(u.z); v[c * 8 + 4] += f.x; v[c * 8 + 5] += f.y;
+    f = unpack_bf16x2(u.w); v[c * 8 + 6] += f.x; v[c * 8 + 7] += f.y;
+  }
+}
+
+// out[b,s,t,p] = LN(emb_pos[p] + emb_len[t] + emb_clip[s] + (p == 0 ? emb_cls : proj[b,s,t,p-1]))
+__global__ void __launch_bounds__(256) video_posembed_ln_kernel(const bf16* __restrict__ proj, const float* __restrict__ emb_cls,
+                                                                const float* __restrict__ emb_pos, const float* __restrict__ emb_len,
+                                                                const float* __restrict__ emb_clip, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps, bf16* __restrict__ out,
+                                                                int B, int S, int T, int P) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long rows = static_cast<long long>(B) * S * T * (P + 1);
+  if (row >= rows) return;
+  const int p = static_cast<int>(row % (P + 1));
+  const long long frame = row / (P + 1);  // (b*S + s)*T + t
+  const int t = static_cast<int>(frame % T);
+  const int s = static_cast<int>((frame / T) % S);
+  float v[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i] = 0.f;
+  if (p == 0) row768_add_f32(v, emb_cls, lane);
+  else row768_add_bf16(v, proj + (frame * P + (p - 1)) * ENC_D, lane);
+  row768_add_f32(v, emb_pos + static_cast<size_t>(p) * ENC_D, lane);
+  row768_add_f32(v, emb_len + static_cast<size_t>(t) * ENC_D, lane);
+  row768_add_f32(v, emb_clip + static_cast<size_t>(s) * ENC_D, lane);
+  row768_ln_store(v, gamma, beta, eps, lane, out + row * ENC_D, nullptr);
+}
+
+// out[b, l] = LN(emb_pos[l] + (l == 0 ? emb_cls : text[b, l-1]))
+template <typename TextT>
+__global__ void __launch_bounds__(256) text_posembed_ln_kernel(const TextT* __restrict__ text, const float* __restrict__ emb_cls,
+                                                               const float* __restrict__ emb_pos, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps, bf16* __restrict__ out,
+                                                               int Bt, int L) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= static_cast<long long>(Bt) * (L + 1)) return;
+  const int l = static_cast<int>(row % (L + 1));
+  const long long b = row / (L + 1);
+  float v[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i] = 0.f;
+  if (l == 0) row768_add_f32(v, emb_cls, lane);
+  else if (sizeof(TextT) == 2) row768_add_bf16(v, reinterpret_cast<const bf16*>(text) + (b * L + (l - 1)) * ENC_D, lane);
+  else row768_add_f32(v, reinterpret_cast<const float*>(text) + (b * L + (l - 1)) * ENC_D, lane);
+  row768_add_f32(v, emb_pos + static_cast<size_t>(l) * ENC_D, lane);
+  row768_ln_store(v, gamma, beta, eps, lane, out + row * ENC_D, nullptr);
+}
+
+// tok_out = LN_f(tok + LN3(h + y))   (one warp per row)
+__global__ void __launch_bounds__(128) recurrent_update_kernel(const float* __restrict__ tok, const float* __restrict__ h,
+                                                               const float* __restrict__ y, const float* __restrict__ g3,
+                                                               const float* __restrict__ b3, const float* __restrict__ gf,
+                                                               const float* __restrict__ bf, float eps, float* __restrict__ tok_out,
+                                                               int rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  float v[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i] = 0.f;
+  row768_add_f32(v, h + static_cast<size_t>(row) * ENC_D, lane);
+  row768_add_f32(v, y + static_cast<size_t>(row) * ENC_D, lane);
+  row768_ln_store(v, g3, b3, eps, lane, nullptr, nullptr);  // v <- LN3(h + y)
+  row768_add_f32(v, tok + static_cast<size_t>(row) * ENC_D, lane);
+  row768_ln_store(v, gf, bf, eps, lane, nullptr, tok_out + static_cast<size_t>(row) * ENC_D);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// skinny linear
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SK_ROWS = 32;
+constexpr int SK_WARPS = 8;
+constexpr int SK_THREADS = SK_WARPS * 32;
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// grid = (ceil(N/8), ceil(rows/32)); dynamic smem = 32*(K+32)*2 + 8*32*8*4
+__global__ void __launch_bounds__(SK_THREADS) skinny_linear_kernel(const float* __restrict__ Xa, const float* __restrict__ Xb,
+                                                                   const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                                   float eps, float* __restrict__ Xout,
+                                                                   const bf16* __restrict__ Wt, const float* __restrict__ bias,
+                                                                   float* __restrict__ Y, int rows, int K, int N, int ldy, int act) {
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  const int pitch = K + 32;  // bf16 elements; (pitch/2) % 32 == 16 words -> conflict-free 16-byte fragment loads
+  bf16* sX = reinterpret_cast<bf16*>(sk_smem);
+  float* sRed = reinterpret_cast<float*>(sk_smem + static_cast<size_t>(SK_ROWS) * pitch * 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r_base = blockIdx.y * SK_ROWS;
+  const int n0 = blockIdx.x * 8;
+
+  // ---- prologue: x = Xa (+ Xb) (-> LayerNorm) ; bf16 copy to smem ; optional fp32 write-back by the first CTA column
+  for (int r = warp; r < SK_ROWS; r += SK_WARPS) {
+    const int row = r_base + r;
+    bf16* dst = sX + static_cast<size_t>(r) * pitch;
+    if (row >= rows) {
+      for (int k = lane * 8; k < K; k += 256) *reinterpret_cast<uint4*>(dst + k) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    if (ln_g != nullptr) {  // K == 768
+      float v[24];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) v[i] = 0.f;
+      row768_add_f32(v, Xa + static_cast<size_t>(row) * K, lane);
+      if (Xb) row768_add_f32(v, Xb + static_cast<size_t>(row) * K, lane);
+      row768_ln_store(v, ln_g, ln_b, eps, lane, dst, (Xout && blockIdx.x == 0) ? Xout + static_cast<size_t>(row) * K : nullptr);
+    } else {
+      for (int k = lane * 8; k < K; k += 256) {
+        const float* a = Xa + static_cast<size_t>(row) * K + k;
+        float4 x0 = __ldg(reinterpret_cast<const float4*>(a)), x1 = __ldg(reinterpret_cast<const float4*>(a + 4));
+        if (Xb) {
+          const float* b = Xb + static_cast<size_t>(row) * K + k;
+          const float4 y0 = __ldg(reinterpret_cast<const float4*>(b)), y1 = __ldg(reinterpret_cast<const float4*>(b + 4));
+          x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
+          x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(x0.x, x0.y); u.y = pack_bf16x2(x0.z, x0.w);
+        u.z = pack_bf16x2(x1.x, x1.y); u.w = pack_bf16x2(x1.z, x1.w);
+        *reinterpret_cast<uint4*>(dst + k) = u;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- main: this warp's K slice; thread (g, t) streams 16 B of weight row n0+g per 32-wide k chunk
+  const int g = lane >> 2, t = lane & 3;
+  const int k_per_warp = K / SK_WARPS;  // multiple of 32 (K in {768, 3072})
+  const int k_begin = warp * k_per_warp;
+  const bf16* wrow = Wt + static_cast<size_t>(n0 + g) * K + k_begin + 8 * t;
+  const bf16* xa0 = sX + static_cast<size_t>(g) * pitch + k_begin + 8 * t;
+  float acc[2][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+  const int n_chunks = k_per_warp / 32;
+#pragma unroll 4
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(wrow + c * 32));
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const uint4 xlo = *reinterpret_cast<const uint4*>(xa0 + static_cast<size_t>(m * 16) * pitch + c * 32);
+      const uint4 xhi = *reinterpret_cast<const uint4*>(xa0 + static_cast<size_t>(m * 16 + 8) * pitch + c * 32);
+      mma16816(acc[m], xlo.x, xhi.x, xlo.y, xhi.y, w.x, w.y);
+      mma16816(acc[m], xlo.z, xhi.z, xlo.w, xhi.w, w.z, w.w);
+    }
+  }
+  // ---- cross-warp K reduction, bias, activation, store
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    float* r = sRed + (warp * SK_ROWS + m * 16 + g) * 8 + 2 * t;
+    r[0] = acc[m][0]; r[1] = acc[m][1];
+    r[8 * 8] = acc[m][2]; r[8 * 8 + 1] = acc[m][3];
+  }
+  __syncthreads();
+  {
+    const int r = tid >> 3, col = tid & 7;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) v += sRed[(w * SK_ROWS + r) * 8 + col];
+    const int row = r_base + r, n = n0 + col;
+    if (row < rows && n < N) {
+      if (bias) v += __ldg(bias + n);
+      if (act == ACT_GELU) v = gelu_erf(v);
+      else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+      Y[static_cast<size_t>(row) * ldy + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cross attention of the single query token: grid = (rows, 3), 4 warps per CTA, one warp per head (12 heads x 64)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CA_MAX_KEYS = 256;
+
+__global__ void __launch_bounds__(128) cross_attention_kernel(const float* __restrict__ q, const bf16* __restrict__ kv_video,
+                                                              const bf16* __restrict__ kv_text, float* __restrict__ ctx,
+                                                              int seg, int S, int Tv, int Lt, int n_cand, int layer,
+                                                              int ld_kv) {
+  __shared__ float sP[4][CA_MAX_KEYS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x, head = blockIdx.y * 4 + warp;
+  const int n_keys = Tv + Lt;
+  const size_t col_k = static_cast<size_t>(layer) * 2 * ENC_D + head * 64;
+  const size_t col_v = col_k + ENC_D;
+  const bf16* vid = kv_video + (static_cast<size_t>(b / n_cand) * S + seg) * Tv * ld_kv;
+  const bf16* txt = kv_text + static_cast<size_t>(b) * Lt * ld_kv;
+  // 8 lanes per key: lane sub-index l8 covers dims [8*l8, 8*l8+8)
+  const int l8 = lane & 7, kslot = lane >> 3;
+  float qv[8];
+  {
+    const float* qp = q + static_cast<size_t>(b) * ENC_D + head * 64 + l8 * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(qp)), c = __ldg(reinterpret_cast<const float4*>(qp + 4));
+    qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = c.x; qv[5] = c.y; qv[6] = c.z; qv[7] = c.w;
+  }
+  float mx = -INFINITY;
+  for (int j0 = 0; j0 < n_keys; j0 += 4) {
+    const int j = j0 + kslot;
+    float d = 0.f;
+    if (j < n_keys) {
+      const bf16* kp = (j < Tv ? vid + static_cast<size_t>(j) * ld_kv : txt + static_cast<size_t>(j - Tv) * ld_kv) + col_k + l8 * 8;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(kp));
+      float2 f;
+      f = unpack_bf16x2(u.x); d += qv[0] * f.x + qv[1] * f.y;
+      f = unpack_bf16x2(u.y); d += qv[2] * f.x + qv[3] * f.y;
+      f = unpack_bf16x2(u.z); d += qv[4] * f.x + qv[5] * f.y;
+      f = unpack_bf16x2(u.w); d += qv[6] * f.x + qv[7] * f.y;
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (j < n_keys) {
+      if (l8 == 0) sP[warp][j] = d;
+      mx = fmaxf(mx, d);
+    }
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < n_keys; j += 32) {
+    const float p = __expf(sP[warp][j] - mx);
+    sP[warp][j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < n_keys; ++j) {
+    const bf16* vp = (j < Tv ? vid + static_cast<size_t>(j) * ld_kv : txt + static_cast<size_t>(j - Tv) * ld_kv) + col_v + 2 * lane;
+    const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(vp)));
+    const float p = sP[warp][j];
+    o0 = fmaf(p, f.x, o0);
+    o1 = fmaf(p, f.y, o1);
+  }
+  float* dst = ctx + static_cast<size_t>(b) * ENC_D + head * 64 + 2 * lane;
+  *reinterpret_cast<float2*>(dst) = make_float2(o0 * inv, o1 * inv);
+}
+
+}  // namespace lrce
+
+using namespace lrce;
+
+extern "C" int lrce_video_posembed_ln(const void* proj, const float* emb_cls, const float* emb_pos, const float* emb_len,
+                                      const float* emb_clip, const float* gamma, const float* beta, float eps, void* out,
+                                      int B, int S, int T, int P, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(proj && emb_cls && emb_pos && emb_len && emb_clip && gamma && beta && out && B > 0 && S > 0 && T > 0 && P > 0,
+               "lrce_video_posembed_ln: bad arguments");
+  const long long rows = static_cast<long long>(B) * S * T * (P + 1);
+  video_posembed_ln_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(proj), emb_cls, emb_pos, emb_len, emb_clip, gamma, beta, eps,
+      reinterpret_cast<bf16*>(out), B, S, T, P);
+  return check_launch("video_posembed_ln_kernel");
+}
+
+extern "C" int lrce_text_posembed_ln(const void* text, int text_fp32, const float* emb_cls, const float* emb_pos, const float* gamma,
+                                     const float* beta, float eps, void* out, int Bt, int L, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(text && emb_cls && emb_pos && gamma && beta && out && Bt > 0 && L > 0, "lrce_text_posembed_ln: bad arguments");
+  const long long rows = static_cast<long long>(Bt) * (L + 1);
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (text_fp32)
+    text_posembed_ln_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(text), emb_cls, emb_pos, gamma, beta,
+                                                          eps, reinterpret_cast<bf16*>(out), Bt, L);
+  else
+    text_posembed_ln_kernel<bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(text), emb_cls, emb_pos, gamma, beta,
+                                                         eps, reinterpret_cast<bf16*>(out), Bt, L);
+  return check_launch("text_posembed_ln_kernel");
+}
+
+extern "C" int lrce_recurrent_update(const float* tok, const float* h, const float* y, const float* g3, const float* b3,
+                                     const float* gf, const float* bf, float eps, float* tok_out, int rows, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(tok && h && y && g3 && b3 && gf && bf && tok_out && rows > 0, "lrce_recurrent_update: bad arguments");
+  recurrent_update_kernel<<<(rows + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tok, h, y, g3, b3, gf, bf, eps,
+                                                                                                tok_out, rows);
+  return check_launch("recurrent_update_kernel");
+}
+
+extern "C" int lrce_skinny_linear(const float* Xa, const float* Xb, const float* ln_gamma, const float* ln_beta, float eps,
+                                  float* Xout, const void* W, const float* bias, float* Y, int rows, int K, int N, int ldy,
+                                  int act, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(Xa && W && Y && rows > 0 && N > 0, "lrce_skinny_linear: bad arguments");
+  LRCE_REQUIRE(K == 768 || K == 3072, "lrce_skinny_linear: K must be 768 or 3072 (got %d)", K);
+  LRCE_REQUIRE(ln_gamma == nullptr || (K == 768 && ln_beta != nullptr), "lrce_skinny_linear: LayerNorm prologue needs K == 768");
+  LRCE_REQUIRE(act >= 0 && act <= 2, "lrce_skinny_linear: unknown activation %d", act);
+  const int smem = SK_ROWS * (K + 32) * 2 + SK_WARPS * SK_ROWS * 8 * 4;
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SK_ROWS * (3072 + 32) * 2 + SK_WARPS * SK_ROWS * 8 * 4);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(skinny_linear_kernel): %s", cudaGetErrorString(e));
+      return LRCE_ECUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((N + 7) / 8, (rows + SK_ROWS - 1) / SK_ROWS);
+  skinny_linear_kernel<<<grid, SK_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      Xa, Xb, ln_gamma, ln_beta, eps, Xout, reinterpret_cast<const bf16*>(W), bias, Y, rows, K, N, ldy, act);
+  return check_launch("skinny_linear_kernel");
+}
+
+extern "C" int lrce_cross_attention(const float* q, const void* kv_video, const void* kv_text, float* ctx, int rows, int seg,
+                                    int S, int Tv, int Lt, int n_cand, int layer, int ld_kv, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(q && kv_video && kv_text && ctx && rows > 0 && n_cand > 0, "lrce_cross_attention: bad arguments");
+  LRCE_REQUIRE(Tv + Lt <= CA_MAX_KEYS, "lrce_cross_attention: %d memory tokens exceed the %d-key limit", Tv + Lt, CA_MAX_KEYS);
+  LRCE_REQUIRE(ld_kv % 8 == 0, "lrce_cross_attention: K/V row pitch must be a multiple of 8");
+  dim3 grid(rows, 3);
+  cross_attention_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      q, reinterpret_cast<const bf16*>(kv_video), reinterpret_cast<const bf16*>(kv_text), ctx, seg, S, Tv, Lt, n_cand, layer,
+      ld_kv);
+  return check_launch("cross_attention_kernel");
+}

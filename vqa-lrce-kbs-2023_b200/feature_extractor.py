@@ -1,0 +1,247 @@
+"""Host-side mirror of lrce/feature_extractor/{video.py, video_swin_ori.py, text.py}: the same module tree, parameter
+names and shapes as the reference (so reference checkpoints load with strict=True), but ``forward`` drives the sm_100a
+kernels of liblrce_b200.so instead of PyTorch ops.
+
+Data layout in HBM: all B*S five-frame segments are processed as ONE batch; activations are bf16, channels-last,
+natural token order ``[segment, d, h, w, C]`` flattened to ``[M, C]`` for the whole backbone — the reference's
+``b c d h w <-> b d h w c`` ping-pong (video_swin_ori.py:428,439,683,685), its window partition/roll copies and its
+per-segment Python loop (video.py:33) do not exist here.
+"""
+import torch
+from torch import nn
+
+from . import ops
+
+SWIN_CKPT = "./pretrained_models/swin_base_patch244_window877_kinetics600_22k.pth"  # e2e.py:11
+
+
+def _relative_position_index(window=(8, 7, 7)):
+    """(392, 392) int64 buffer kept for state_dict compatibility (video_swin_ori.py:134-148); the kernels use the closed
+    form f(i) - f(j) + 1267 instead of this table."""
+    wd, wh, ww = window
+    d, h, w = torch.meshgrid(torch.arange(wd), torch.arange(wh), torch.arange(ww), indexing="ij")
+    d, h, w = d.reshape(-1), h.reshape(-1), w.reshape(-1)
+    return ((d[:, None] - d[None, :] + wd - 1) * ((2 * wh - 1) * (2 * ww - 1))
+            + (h[:, None] - h[None, :] + wh - 1) * (2 * ww - 1) + (w[:, None] - w[None, :] + ww - 1))
+
+
+class _Holder(nn.Module):
+    """parameter container: children are only there to own correctly named parameters"""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter holder; the forward pass runs in SwinTransformer3D.forward via liblrce_b200")
+
+
+class WindowAttention3D(_Holder):
+    def __init__(self, dim, window_size, num_heads):
+        super().__init__()
+        table = (2 * window_size[0] - 1) * (2 * window_size[1] - 1) * (2 * window_size[2] - 1)
+        self.relative_position_bias_table = nn.Parameter(torch.zeros(table, num_heads))
+        self.register_buffer("relative_position_index", _relative_position_index(window_size))
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+
+class Mlp(_Holder):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class SwinTransformerBlock3D(_Holder):
+    def __init__(self, dim, num_heads, window_size):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = WindowAttention3D(dim, window_size, num_heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = Mlp(dim, 4 * dim)
+
+
+class PatchMerging(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = nn.LayerNorm(4 * dim)
+
+
+class BasicLayer(_Holder):
+    def __init__(self, dim, depth, num_heads, window_size, downsample):
+        super().__init__()
+        self.blocks = nn.ModuleList([SwinTransformerBlock3D(dim, num_heads, window_size) for _ in range(depth)])
+        self.downsample = PatchMerging(dim) if downsample else None
+
+
+class PatchEmbed3D(_Holder):
+    def __init__(self, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = nn.LayerNorm(embed_dim)
+
+
+class _PackedWeights:
+    """bf16 / fp32 device copies of the parameters in the layout the kernels consume, rebuilt when any parameter
+    changes (optimizer step, load_state_dict, .to())."""
+
+    def __init__(self):
+        self.sig = None
+        self.data = None
+
+    @staticmethod
+    def signature(module):
+        s = 0
+        dev = None
+        for p in module.parameters():
+            s += p._version + (p.data_ptr() & 0xFFFF)
+            dev = p.device
+        return (s, dev)
+
+
+class SwinTransformer3D(nn.Module):
+    """Video Swin backbone with the reference's constructor arguments used by VideoExtractor (video.py:10-18).
+    forward: clips fp32 (n, T, 3, H, W) in [0,1] (un-normalised, frames-major as the dataset yields them) ->
+    features (n, D, H/32, W/32, 8*embed) bf16 channels-last, final LayerNorm applied (video_swin_ori.py:674-687)."""
+
+    def __init__(self, embed_dim=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32), patch_size=(2, 4, 4),
+                 window_size=(8, 7, 7), drop_path_rate=0.2, patch_norm=True, in_chans=3):
+        super().__init__()
+        assert tuple(patch_size) == (2, 4, 4) and tuple(window_size) == (8, 7, 7) and patch_norm and embed_dim == 128, \
+            "liblrce_b200 is specialised for the Swin-B configuration LRCE uses (video.py:10-18)"
+        self.embed_dim, self.depths, self.num_heads = embed_dim, tuple(depths), tuple(num_heads)
+        self.patch_size, self.window_size = tuple(patch_size), tuple(window_size)
+        self.drop_path_rate = drop_path_rate  # stochastic depth is identity in eval; the kernels are forward/eval only
+        self.patch_embed = PatchEmbed3D(patch_size, in_chans, embed_dim)
+        self.layers = nn.ModuleList([
+            BasicLayer(embed_dim << i, depths[i], num_heads[i], window_size, downsample=i < len(depths) - 1)
+            for i in range(len(depths))])
+        self.num_features = embed_dim << (len(depths) - 1)
+        self.norm = nn.LayerNorm(self.num_features)
+        self._packed = _PackedWeights()
+        self.init_weights()
+
+    def init_weights(self, pretrained=None):
+        """same initialisation as the reference (video_swin_ori.py:647-654)"""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def packed(self):
+        sig = _PackedWeights.signature(self)
+        if self._packed.sig != sig:
+            self._packed.data = self._pack()
+            self._packed.sig = sig
+        return self._packed.data
+
+    @torch.no_grad()
+    def _pack(self):
+        dev = self.norm.weight.device
+        if dev.type != "cuda":
+            raise ops._lib.LrceError("SwinTransformer3D parameters must live on a CUDA device (no CPU fallback)")
+        bf = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        pk = {"pe_w": bf(self.patch_embed.proj.weight.reshape(self.embed_dim, -1)), "pe_b": f32(self.patch_embed.proj.bias),
+              "pe_g": f32(self.patch_embed.norm.weight), "pe_beta": f32(self.patch_embed.norm.bias),
+              "norm_g": f32(self.norm.weight), "norm_b": f32(self.norm.bias), "stages": []}
+        for layer in self.layers:
+            blocks = []
+            for blk in layer.blocks:
+                blocks.append(dict(
+                    n1g=f32(blk.norm1.weight), n1b=f32(blk.norm1.bias), n2g=f32(blk.norm2.weight), n2b=f32(blk.norm2.bias),
+                    wqkv=bf(blk.attn.qkv.weight), bqkv=f32(blk.attn.qkv.bias), wproj=bf(blk.attn.proj.weight),
+                    bproj=f32(blk.attn.proj.bias), w1=bf(blk.mlp.fc1.weight), b1=f32(blk.mlp.fc1.bias),
+                    w2=bf(blk.mlp.fc2.weight), b2=f32(blk.mlp.fc2.bias),
+                    bias=ops.window_bias_pack(f32(blk.attn.relative_position_bias_table))))
+            ds = None
+            if layer.downsample is not None:
+                ds = dict(g=f32(layer.downsample.norm.weight), b=f32(layer.downsample.norm.bias),
+                          w=bf(layer.downsample.reduction.weight))
+            pk["stages"].append(dict(blocks=blocks, ds=ds))
+        return pk
+
+    # ---------------------------------------------------------------------------------------------------------
+    def forward(self, clips, taps=None, out_fp32=False):
+        if clips.dim() != 5 or clips.shape[2] != 3:
+            raise ops._lib.LrceError(f"expected clips (n, T, 3, H, W), got {tuple(clips.shape)}")
+        n, T, _, Hin, Win = clips.shape
+        pk = self.packed()
+        clips = clips.contiguous().float()
+        D, H, W = (T + 1) // 2, Hin // 4, Win // 4
+        if D != 3 or H % 7 or W % 7:
+            raise ops._lib.LrceError("the window-attention kernel needs 5/6-frame segments and H, W multiples of 28")
+        a = ops.patch_gather(clips)
+        x = ops.gemm(a, pk["pe_w"], pk["pe_b"], epilogue=ops.EPI_BIAS_LN, ln=(pk["pe_g"], pk["pe_beta"], 1e-5))
+        if taps is not None:
+            taps["patch_embed"] = x.view(n, D, H, W, -1).clone()
+        C = self.embed_dim
+        for i, st in enumerate(pk["stages"]):
+            heads = self.num_heads[i]
+            shift = (3, 3) if H > 7 else (0, 0)  # clamped axes are never shifted (video_swin_ori.py:91-104)
+            for j, b in enumerate(st["blocks"]):
+                xn = ops.layernorm(x, b["n1g"], b["n1b"], 1e-5)
+                qkv = ops.gemm(xn, b["wqkv"], b["bqkv"])
+                att = ops.window_attention(qkv, b["bias"], n, D, H, W, C, heads, shift if j % 2 else (0, 0), out=xn)
+                del qkv
+                ops.gemm(att, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x)
+                xn = ops.layernorm(x, b["n2g"], b["n2b"], 1e-5, out=att)
+                hid = ops.gemm(xn, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU)
+                ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x)
+                del hid
+                if taps is not None and j < 2 and i < 3:
+                    taps[f"stage{i}.block{j}"] = x.view(n, D, H, W, C).clone()
+            if st["ds"] is not None:
+                y = ops.patch_merge_ln(x, st["ds"]["g"], st["ds"]["b"], 1e-5, n, D, H, W, C)
+                x = ops.gemm(y, st["ds"]["w"], None)
+                H, W, C = H // 2, W // 2, 2 * C
+            if taps is not None:
+                taps[f"stage{i}.out"] = x.view(n, D, H, W, C).clone()
+        out = ops.layernorm(x, pk["norm_g"], pk["norm_b"], 1e-5, out_fp32=out_fp32)
+        return out.view(n, D, H, W, C)
+
+    def train(self, mode=True):
+        # the reference's override returns None (video_swin_ori.py:689-692); nn.Module semantics are kept here
+        return super().train(mode)
+
+
+class VideoExtractor(nn.Module):
+    """Drop-in for lrce.feature_extractor.video.VideoExtractor (video.py:6-43).
+    forward: (B, S, T=5, 3, 224, 224) fp32 in [0,1] -> (B, S, 3, 49, 1024) bf16."""
+
+    def __init__(self, ckpt_path=None):
+        super().__init__()
+        self.swin = SwinTransformer3D(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], patch_size=(2, 4, 4),
+                                      window_size=(8, 7, 7), drop_path_rate=0.2, patch_norm=True)
+        if ckpt_path is not None:
+            checkpoint = torch.load(ckpt_path, map_location="cpu")
+            sd = {k[9:]: v for k, v in checkpoint["state_dict"].items() if "backbone" in k}  # video.py:21-26
+            self.swin.load_state_dict(sd)
+
+    def forward(self, clips, taps=None, out_fp32=False):
+        B, S, T = clips.shape[:3]
+        f = self.swin(clips.reshape((B * S,) + tuple(clips.shape[2:])), taps=taps, out_fp32=out_fp32)
+        return f.view(B, S, f.shape[1], f.shape[2] * f.shape[3], f.shape[4])
+
+
+class TextExtractor(nn.Module):
+    """lrce.feature_extractor.text.TextExtractor (text.py:5-17): HF BertModel, unchanged PyTorch.
+    Runs under bf16 autocast regardless of the ambient autocast dtype."""
+
+    def __init__(self, pretrained=True):
+        super().__init__()
+        import transformers
+
+        if pretrained:
+            self.bert = transformers.BertModel.from_pretrained("bert-base-uncased")
+        else:
+            self.bert = transformers.BertModel(transformers.BertConfig())
+
+    def forward(self, input_ids, attention_mask, token_type_ids):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return self.bert(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids,
+                             output_hidden_states=False).last_hidden_state

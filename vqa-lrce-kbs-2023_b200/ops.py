@@ -5,6 +5,12 @@ import torch
 from . import _lib
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_LN = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+WINDOW = (3, 7, 7)  # effective Swin window on LRCE's 5-frame segments
+BIAS_PITCH = 152
+
+# count of kernels launched through this module (bench.py reports it as gpu_launches)
+launches = 0
 
 
 def _ptr(t):
@@ -22,6 +28,27 @@ def _req(t, dtype, name):
         raise _lib.LrceError(f"{name} must be a CUDA tensor: the LRCE hot path has no CPU fallback")
     if t.dtype != dtype:
         raise _lib.LrceError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous() and t.dim() != 2:
+        raise _lib.LrceError(f"{name} must be contiguous")
+
+
+# when `trace` is a list, every launch is bracketed by CUDA events on the launching stream and appended as
+# (entry point, tag, flops, bytes, start_event, end_event); bench.py uses it for the per-kernel roofline figures
+trace = None
+
+
+def _call(name, *args, work=None):
+    global launches
+    launches += 1
+    if trace is None:
+        _lib.check(getattr(_lib.lib(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+    e1.record()
+    tag, flops, nbytes = work if work is not None else ("", 0, 0)
+    trace.append((name, tag, flops, nbytes, e0, e1))
 
 
 def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, residual=None, out=None, out_fp32=False, ln=None):
@@ -39,9 +66,136 @@ def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, residual=None, out=None, out_fp3
     if ln is not None:
         g, b, eps = ln
         _req(g, torch.float32, "ln gamma"); _req(b, torch.float32, "ln beta")
-    rc = _lib.lib().lrce_gemm_bf16(
-        _ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(bias), _ptr(residual),
-        residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), epilogue, int(out_fp32),
-        _ptr(g), _ptr(b), float(eps), _stream())
-    _lib.check(rc, "lrce_gemm_bf16")
+    _call("lrce_gemm_bf16", _ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(bias), _ptr(residual),
+          residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), epilogue, int(out_fp32),
+          _ptr(g), _ptr(b), float(eps), _stream(),
+          work=(f"M{M}N{N}K{K}e{epilogue}", 2.0 * M * N * K,
+                2.0 * (M * K + N * K + M * N * (2 if residual is not None else 1)) * (2 if out_fp32 else 1)))
+    return out
+
+
+def layernorm(x, gamma, beta, eps, *, out=None, out_fp32=False):
+    """x bf16 (rows, C) contiguous -> LayerNorm over C."""
+    _req(x, torch.bfloat16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    _call("lrce_layernorm_bf16", _ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), float(eps), rows, C, int(out_fp32), _stream(),
+          work=(f"C{C}", 8.0 * rows * C, rows * C * (6.0 if out_fp32 else 4.0)))
+    return out
+
+
+def patch_merge_ln(x, gamma, beta, eps, n_seg, D, H, W, C):
+    """x bf16 [n_seg*D*H*W, C] -> bf16 [n_seg*D*(H/2)*(W/2), 4C] (2x2 gather + LayerNorm)."""
+    _req(x, torch.bfloat16, "x")
+    assert x.is_contiguous() and x.numel() == n_seg * D * H * W * C
+    out = torch.empty((n_seg * D * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=torch.bfloat16)
+    _call("lrce_patch_merge_ln_bf16", _ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), float(eps), n_seg, D, H, W, C, _stream(),
+          work=(f"C{C}", 8.0 * x.numel(), 4.0 * x.numel()))
+    return out
+
+
+def patch_gather(clips):
+    """clips fp32 (n_seg, T, 3, Hin, Win) -> bf16 [n_seg*ceil(T/2)*(Hin/4)*(Win/4), 96]."""
+    _req(clips, torch.float32, "clips")
+    assert clips.is_contiguous() and clips.dim() == 5 and clips.shape[2] == 3
+    n, T, _, Hin, Win = clips.shape
+    out = torch.empty((n * ((T + 1) // 2) * (Hin // 4) * (Win // 4), 96), device=clips.device, dtype=torch.bfloat16)
+    _call("lrce_patch_gather_f32", _ptr(clips), _ptr(out), n, T, Hin, Win, _stream(),
+          work=("", 2.0 * clips.numel(), 4.0 * clips.numel() + 2.0 * out.numel()))
+    return out
+
+
+def window_remap(x, n_seg, dims, window, shift, inverse=False):
+    """x bf16 [n_seg*D*H*W, C] -> same shape, rows permuted by shift+partition (or its inverse)."""
+    _req(x, torch.bfloat16, "x")
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    _call("lrce_window_remap_bf16", _ptr(x), _ptr(out), n_seg, *dims, x.shape[-1], *window, *shift, int(inverse), _stream(),
+          work=(f"C{x.shape[-1]}", 0.0, 4.0 * x.numel()))
+    return out
+
+
+def remap_index(dims, window, shift, device="cuda"):
+    """(gather [nWin, N], region [nWin, N], relpos [N]) int32 tables from the kernels' own index functions."""
+    n = dims[0] * dims[1] * dims[2]
+    N = window[0] * window[1] * window[2]
+    gather = torch.empty((n // N, N), device=device, dtype=torch.int32)
+    region = torch.empty((n // N, N), device=device, dtype=torch.int32)
+    relpos = torch.empty((N,), device=device, dtype=torch.int32)
+    _call("lrce_remap_index", _ptr(gather), _ptr(region), _ptr(relpos), *dims, *window, *shift, _stream())
+    return gather, region, relpos
+
+
+def window_bias_pack(table):
+    """relative_position_bias_table fp32 [2535, nH] -> dense bf16 [nH, 147, 152] (pre-multiplied by log2 e)."""
+    _req(table, torch.float32, "table")
+    assert table.is_contiguous() and table.shape[0] == 2535
+    nh = table.shape[1]
+    out = torch.empty((nh, 147, BIAS_PITCH), device=table.device, dtype=torch.bfloat16)
+    _call("lrce_window_bias_pack", _ptr(table), _ptr(out), nh, _stream())
+    return out
+
+
+def window_attention(qkv, bias_dense, n_seg, D, H, W, C, n_heads, shift_hw, out=None):
+    """qkv bf16 [n_seg*D*H*W, 3C] (natural order) -> bf16 [n_seg*D*H*W, C] (natural order)."""
+    _req(qkv, torch.bfloat16, "qkv"); _req(bias_dense, torch.bfloat16, "bias_dense")
+    assert qkv.is_contiguous() and qkv.shape == (n_seg * D * H * W, 3 * C)
+    if out is None:
+        out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.bfloat16)
+    _call("lrce_window_attention_bf16", _ptr(qkv), _ptr(out), _ptr(bias_dense), n_seg, D, H, W, C, n_heads,
+          shift_hw[0], shift_hw[1], _stream(),
+          # core FLOPs as SURVEY.md 8(d) counts them: QK^T + PV = 4 * 147^2 * 32 per (window, head)
+          work=(f"C{C}", 4.0 * 147 * 147 * 32 * (qkv.shape[0] // 147) * n_heads, 2.0 * qkv.numel() + 2.0 * out.numel()))
+    return out
+
+
+def video_posembed_ln(proj, emb_cls, emb_pos, emb_len, emb_clip, gamma, beta, eps, B, S, T, P):
+    _req(proj, torch.bfloat16, "proj")
+    assert proj.is_contiguous() and proj.shape == (B * S * T * P, 768)
+    out = torch.empty((B, S, T * (P + 1), 768), device=proj.device, dtype=torch.bfloat16)
+    _call("lrce_video_posembed_ln", _ptr(proj), _ptr(emb_cls), _ptr(emb_pos), _ptr(emb_len), _ptr(emb_clip), _ptr(gamma),
+          _ptr(beta), float(eps), _ptr(out), B, S, T, P, _stream())
+    return out
+
+
+def text_posembed_ln(text, emb_cls, emb_pos, gamma, beta, eps):
+    if text.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.LrceError(f"text features must be bf16 or fp32, got {text.dtype}")
+    _req(text, text.dtype, "text")
+    assert text.is_contiguous() and text.dim() == 3 and text.shape[2] == 768
+    Bt, L, _ = text.shape
+    out = torch.empty((Bt, L + 1, 768), device=text.device, dtype=torch.bfloat16)
+    _call("lrce_text_posembed_ln", _ptr(text), int(text.dtype == torch.float32), _ptr(emb_cls), _ptr(emb_pos), _ptr(gamma), _ptr(beta), float(eps), _ptr(out),
+          Bt, L, _stream())
+    return out
+
+
+def skinny_linear(xa, w, bias, out, n_out, *, xb=None, ln=None, xout=None, act=ACT_NONE, eps=1e-12):
+    """out[rows, n_out] fp32 = act(LN?(xa + xb) @ w.T + bias); w bf16 [ceil(n_out/8)*8, K]."""
+    _req(xa, torch.float32, "xa"); _req(xb, torch.float32, "xb"); _req(w, torch.bfloat16, "w")
+    _req(out, torch.float32, "out"); _req(xout, torch.float32, "xout")
+    rows, K = xa.shape
+    assert xa.is_contiguous() and w.is_contiguous() and w.shape[1] == K and w.shape[0] >= n_out and w.shape[0] % 8 == 0
+    assert out.stride(1) == 1 and out.shape[0] == rows
+    g, b = ln if ln is not None else (None, None)
+    _call("lrce_skinny_linear", _ptr(xa), _ptr(xb), _ptr(g), _ptr(b), float(eps), _ptr(xout), _ptr(w), _ptr(bias),
+          _ptr(out), rows, K, n_out, out.stride(0), act, _stream())
+    return out
+
+
+def cross_attention(q, kv_video, kv_text, ctx, seg, S, Tv, Lt, n_cand, layer):
+    _req(q, torch.float32, "q"); _req(kv_video, torch.bfloat16, "kv_video"); _req(kv_text, torch.bfloat16, "kv_text")
+    rows = q.shape[0]
+    assert kv_video.stride(0) == kv_text.stride(0)
+    _call("lrce_cross_attention", _ptr(q), _ptr(kv_video), _ptr(kv_text), _ptr(ctx), rows, seg, S, Tv, Lt, n_cand, layer,
+          kv_video.stride(0), _stream())
+    return ctx
+
+
+def recurrent_update(tok, h, y, g3, b3, gf, bf, eps, out):
+    _call("lrce_recurrent_update", _ptr(tok), _ptr(h), _ptr(y), _ptr(g3), _ptr(b3), _ptr(gf), _ptr(bf), float(eps),
+          _ptr(out), tok.shape[0], _stream())
     return out

@@ -111,19 +111,20 @@ int lrce_text_posembed_ln(const void* text, int text_fp32, const float* emb_cls,
 #define LRCE_ACT_GELU 1
 #define LRCE_ACT_RELU 2
 
-/* Y[rows, N] (fp32, pitch ldy) = act(X W^T + bias) with X = Xa (+ Xb), optionally LayerNorm'ed (ln_gamma != NULL,
- * K == 768; the normalised X is also written to Xout fp32 when non-NULL). X fp32 [rows, K], K in {768, 3072};
- * W bf16 with ceil(N/8)*8 rows of K. The summarisation-token path of nn.TransformerDecoderLayer (post-norm) and
- * final_fc: replaces fusionv3.py:46 (per-layer linears + norms on the 1-token target) and :195. */
-int lrce_skinny_linear(const float* Xa, const float* Xb, const float* ln_gamma, const float* ln_beta, float eps,
-                       float* Xout, const void* W, const float* bias, float* Y, int rows, int K, int N, int ldy, int act,
-                       void* stream);
+/* Y[rows, N] (pitch ldy; fp32, or bf16 when y_bf16 != 0) = act(X W^T + bias) with X = Xa (+ Xb), optionally
+ * LayerNorm'ed (ln_gamma != NULL, K == 768; the normalised X is also written to Xout fp32 when non-NULL). Xa is fp32
+ * [rows, K], or bf16 when xa_bf16 != 0 (then Xb and ln_gamma must be NULL); K in {768, 3072}; W bf16 with
+ * ceil(N/8)*8 rows of K. The summarisation-token path of nn.TransformerDecoderLayer (post-norm) and final_fc:
+ * replaces fusionv3.py:46 (per-layer linears + norms on the 1-token target) and :195. */
+int lrce_skinny_linear(const void* Xa, int xa_bf16, const float* Xb, const float* ln_gamma, const float* ln_beta, float eps,
+                       float* Xout, const void* W, const float* bias, void* Y, int y_bf16, int rows, int K, int N, int ldy,
+                       int act, void* stream);
 
-/* ctx[rows, 768] = softmax(q K^T) V for one query token per row over the memory [video segment `seg` (Tv tokens) ; text
+/* ctx[rows, 768] (bf16) = softmax(q K^T) V for one query token per row over the memory [video segment `seg` (Tv tokens) ; text
  * (Lt tokens)], 12 heads x 64; q fp32 already scaled by 1/8. kv_video bf16 [(rows/n_cand)*S*Tv, ld_kv], kv_text bf16
  * [rows*Lt, ld_kv], K at column layer*1536 + head*64, V at +768. Replaces the multihead_attn call inside
  * nn.TransformerDecoderLayer (fusionv3.py:45-46; candidate expansion fusionv3.py:259). */
-int lrce_cross_attention(const float* q, const void* kv_video, const void* kv_text, float* ctx, int rows, int seg, int S,
+int lrce_cross_attention(const float* q, const void* kv_video, const void* kv_text, void* ctx, int rows, int seg, int S,
                          int Tv, int Lt, int n_cand, int layer, int ld_kv, void* stream);
 
 /* tok_out = LN_f(tok + LN_3(h + y)): closes the 12th decoder layer and the recurrent step (fusionv3.py:47-48). */

@@ -1,0 +1,31 @@
+"""GPU probe: window-attention kernel timing per Swin stage (CUDA events), config-2 shapes (96 segments)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import lrce_b200
+from lrce_b200 import ops
+
+n_seg = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+stages = [("s1", 56, 128, 4), ("s2", 28, 256, 8), ("s3", 14, 512, 16), ("s4", 7, 1024, 32)]
+only = sys.argv[2] if len(sys.argv) > 2 else None
+for name, hw, C, heads in stages:
+    if only and name != only:
+        continue
+    T = 3 * hw * hw
+    qkv = (torch.randn(n_seg * T, 3 * C, device="cuda") * 1.0).bfloat16()
+    bias = ops.window_bias_pack(torch.randn(2535, heads, device="cuda") * 0.5)
+    out = torch.empty(n_seg * T, C, device="cuda", dtype=torch.bfloat16)
+    for shift in ((0, 0), (3, 3) if hw > 7 else (0, 0)):
+        for _ in range(2):
+            ops.window_attention(qkv, bias, n_seg, 3, hw, hw, C, heads, shift, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        iters = 5
+        for _ in range(iters):
+            ops.window_attention(qkv, bias, n_seg, 3, hw, hw, C, heads, shift, out=out)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        items = n_seg * (hw // 7) ** 2 * heads
+        flops = items * 4.0 * 147 * 147 * 32
+        byts = qkv.numel() * 2 + out.numel() * 2
+        print(f"{name} shift={shift} {ms*1e3:8.1f} us  items={items} core {flops/ms/1e9:6.1f} TFLOP/s  {byts/ms/1e6:7.1f} GB/s  {ms*1e6/items*296:.0f} ns/item/CTA", flush=True)

@@ -27,7 +27,7 @@ _SIGNATURES = {
     "lrce_window_attention_bf16": [_vp, _vp, _vp] + [_i] * 8 + [_vp],
     "lrce_video_posembed_ln": [_vp] * 7 + [_f, _vp, _i, _i, _i, _i, _vp],
     "lrce_text_posembed_ln": [_vp, _i] + [_vp] * 4 + [_f, _vp, _i, _i, _vp],
-    "lrce_skinny_linear": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "lrce_skinny_linear": [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "lrce_cross_attention": [_vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
     "lrce_recurrent_update": [_vp] * 7 + [_f, _vp, _i, _vp],
 }

@@ -37,9 +37,24 @@ class E2EBase(nn.Module):
     def forward(self, video_clips, texts, texts_attention_mask, texts_type_ids):
         if not video_clips.is_cuda:
             raise ops._lib.LrceError("E2E forward needs CUDA inputs on a B200: the hot path has no CPU fallback")
+        # The two extractors are independent (e2e.py:23-24). Swin's ~170 long kernels are enqueued first on the current
+        # stream; BERT's ~200 short library kernels then go to a side stream, so they run inside Swin's shadow instead
+        # of in front of it, and their launch overhead is hidden too.
+        cur = torch.cuda.current_stream()
+        side = self._side_stream(video_clips.device)
+        side.wait_stream(cur)
         video_features = self.extract_video_features(video_clips)
-        texts_features = self.extract_text_features(texts, texts_attention_mask, texts_type_ids)
+        with torch.cuda.stream(side):
+            texts_features = self.extract_text_features(texts, texts_attention_mask, texts_type_ids)
+        cur.wait_stream(side)
+        texts_features.record_stream(cur)
         return self.fusion_model(video_features, texts_features, texts_attention_mask)
+
+    def _side_stream(self, device):
+        s = getattr(self, "_side", None)
+        if s is None or s.device != device:
+            s = self._side = torch.cuda.Stream(device=device)
+        return s
 
 
 class E2EOpenEnded(E2EBase):

@@ -174,20 +174,24 @@ def text_posembed_ln(text, emb_cls, emb_pos, gamma, beta, eps):
 
 
 def skinny_linear(xa, w, bias, out, n_out, *, xb=None, ln=None, xout=None, act=ACT_NONE, eps=1e-12):
-    """out[rows, n_out] fp32 = act(LN?(xa + xb) @ w.T + bias); w bf16 [ceil(n_out/8)*8, K]."""
-    _req(xa, torch.float32, "xa"); _req(xb, torch.float32, "xb"); _req(w, torch.bfloat16, "w")
-    _req(out, torch.float32, "out"); _req(xout, torch.float32, "xout")
+    """out[rows, n_out] (fp32 or bf16) = act(LN?(xa + xb) @ w.T + bias); xa fp32 or bf16; w bf16 [ceil(n_out/8)*8, K]."""
+    _req(xb, torch.float32, "xb"); _req(w, torch.bfloat16, "w"); _req(xout, torch.float32, "xout")
+    if xa.dtype not in (torch.float32, torch.bfloat16) or out.dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.LrceError("skinny_linear: xa / out must be fp32 or bf16")
+    _req(xa, xa.dtype, "xa"); _req(out, out.dtype, "out")
     rows, K = xa.shape
     assert xa.is_contiguous() and w.is_contiguous() and w.shape[1] == K and w.shape[0] >= n_out and w.shape[0] % 8 == 0
     assert out.stride(1) == 1 and out.shape[0] == rows
     g, b = ln if ln is not None else (None, None)
-    _call("lrce_skinny_linear", _ptr(xa), _ptr(xb), _ptr(g), _ptr(b), float(eps), _ptr(xout), _ptr(w), _ptr(bias),
-          _ptr(out), rows, K, n_out, out.stride(0), act, _stream())
+    _call("lrce_skinny_linear", _ptr(xa), int(xa.dtype == torch.bfloat16), _ptr(xb), _ptr(g), _ptr(b), float(eps),
+          _ptr(xout), _ptr(w), _ptr(bias), _ptr(out), int(out.dtype == torch.bfloat16), rows, K, n_out, out.stride(0),
+          act, _stream(), work=(f"K{K}N{n_out}", 2.0 * rows * K * n_out, 2.0 * K * n_out))
     return out
 
 
 def cross_attention(q, kv_video, kv_text, ctx, seg, S, Tv, Lt, n_cand, layer):
     _req(q, torch.float32, "q"); _req(kv_video, torch.bfloat16, "kv_video"); _req(kv_text, torch.bfloat16, "kv_text")
+    _req(ctx, torch.bfloat16, "ctx")
     rows = q.shape[0]
     assert kv_video.stride(0) == kv_text.stride(0)
     _call("lrce_cross_attention", _ptr(q), _ptr(kv_video), _ptr(kv_text), _ptr(ctx), rows, seg, S, Tv, Lt, n_cand, layer,

@@ -141,7 +141,9 @@ def _attention_reference(qkv, table, dims, heads, shift):
     return out
 
 
-@pytest.mark.parametrize("name,C,heads,n_seg", [("s1", 128, 4, 2), ("s2", 256, 8, 2), ("s3", 512, 16, 3), ("s4", 1024, 32, 5)])
+# the last two cases give every persistent CTA 10-17 work units (deep pipeline state, head switches inside a CTA)
+@pytest.mark.parametrize("name,C,heads,n_seg", [("s1", 128, 4, 2), ("s2", 256, 8, 2), ("s3", 512, 16, 3), ("s4", 1024, 32, 5),
+                                                ("s3", 512, 16, 40), ("s2", 256, 8, 12)])
 @pytest.mark.parametrize("shifted", [False, True])
 def test_window_attention(ops, name, C, heads, n_seg, shifted):
     dims = STAGES[name]

@@ -149,8 +149,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool TMA_STORE = (sizeof(OutT) == 2) && (EPI != EPI_BIAS_LN);
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment is required by the 128B swizzle atoms; the pointer stays derived from the __shared__ array so
+  // that the epilogue's slab writes compile to STS (an integer round trip would demote them to generic stores)
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* sC = sB + STAGES * Cfg::B_BYTES;  // 2 output slabs, 1024-byte aligned (stage sizes are multiples of 1024)

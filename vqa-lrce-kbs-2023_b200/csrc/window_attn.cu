@@ -1,220 +1,361 @@
-// window_attn.cu — (shifted-)window multi-head attention core of Video Swin (video_swin_ori.py:166-186) with the
-// cyclic shift / window_partition / window_reverse remap (video_swin_ori.py:262-276) fused into its loads and stores.
+// window_attn.cu — (shifted-)window multi-head attention core of Video Swin (video_swin_ori.py:166-186) on tcgen05
+// tensor cores, with the cyclic shift / window_partition / window_reverse remap (video_swin_ori.py:262-276) fused into
+// its loads and stores.
 //
 // Input  : qkv  bf16 [n_seg * D*H*W, 3C] in NATURAL token order (the qkv Linear is per token, so it runs before any
 //          partition); column layout [q | k | v][head][32] (video_swin_ori.py:165).
 // Output : out  bf16 [n_seg * D*H*W, C] in natural token order, heads merged (video_swin_ori.py:186), i.e. exactly
 //          roll(window_reverse(attn @ v), +shift) — the proj GEMM + residual then runs with no remap at all.
 //
-// One CTA owns one head and walks a strided list of (segment, window) items:
-//   * the head's dense relative-position bias (147 x 152 bf16, pre-multiplied by log2 e) stays resident in smem;
-//   * per item the 147 q/k/v rows of the window are gathered from their rolled source tokens with 16-byte cp.async
-//     (index = window_source_token(), the same function lrce_remap_index() exports for the bit-exact test);
-//   * each warp takes 16-row stripes: S = q k^T on mma.sync m16n8k16 (bf16, fp32 accumulate), + bias, + shift mask
-//     (-100 where region ids differ, video_swin_ori.py:357-358), exp2-softmax in registers, P v with P re-used
-//     straight from the accumulator registers, 1/rowsum, and a scatter of 64-byte rows through the inverse remap.
-// N = 147 is padded to 160 query rows / 152 key columns; padded keys are forced to -inf, padded rows never stored.
+// One persistent CTA per SM walks a contiguous range of (head, segment, window) work units; 14 warps:
+//   warps 9,10,13 loaders: one warp each for q, k and v: gather the window's 147 rows (64 B each) from their rolled
+//                          source tokens with 16-byte cp.async (4 lanes per row -> full 32-byte sectors) into UMMA
+//                          "core matrix" order (8 rows x 16 B contiguous), double-buffered; q/k buffers are recycled
+//                          as soon as S has been computed, v buffers after P v; the row index is
+//                          window_source_token(), the function lrce_remap_index() exports for the bit-exact test
+//   warp  11     MMA     : one thread issues S = q k^T (2 row tiles x [M=128, N=160, K=32]) and O = P v (2 x [M=128,
+//                          N=32, K=160], v consumed MN-major exactly as it sits in memory) with tcgen05.mma into TMEM
+//   warps 0-8,12 softmax : thread-per-row on the TMEM accumulator (two warps split the 160 columns of each 32-row
+//                          quarter): t = s*scale*log2e + bias (dense 147x152 bf16 table of this head, resident in
+//                          smem) + shift mask (-100 where region ids differ, video_swin_ori.py:357-358); row max;
+//                          p = exp2(t - max) written as bf16 A-operand tiles to smem; 1/rowsum applied to O in the
+//                          epilogue, which scatters 32-byte row pieces through the inverse remap.
+// S(i+1) and P v(i) run on the tensor core while the softmax warps are still busy with item i's epilogue / item i+1's
+// first pass, so the kernel is bound by the softmax ALU work, not by the MMAs. N = 147 is padded to 2 x 128 query rows
+// and 160 key columns; padded keys get p = 0, padded rows are never stored.
 #include "host_common.h"
 #include "lrce_common.cuh"
 #include "remap.cuh"
 
 namespace lrce {
 
-constexpr int WA_N = 147;
-constexpr int WA_ROWS = 160;     // 10 stripes of 16 query rows
-constexpr int WA_KTILES = 19;    // 152 key columns
-constexpr int WA_PITCH = 40;     // smem row pitch in bf16 (32 + 8 pad -> 80 B, conflict-free ldmatrix)
-constexpr int WA_BIAS_PITCH = 152;
-constexpr int WA_WARPS = 5;
-constexpr int WA_THREADS = WA_WARPS * 32;
-constexpr int WA_SMEM = 3 * WA_ROWS * WA_PITCH * 2 + WA_N * WA_BIAS_PITCH * 2 + WA_ROWS * 4 + WA_ROWS;
+constexpr int WA_N = 147;           // tokens per (3,7,7) window
+constexpr int WA_KEYS = 160;        // key columns of the S tile (multiple of 16)
+constexpr int WA_BIAS_PITCH = 152;  // dense bias row pitch (bf16)
+constexpr int WA_THREADS = 14 * 32;
 
-__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(smem_u32(p)));
+// shared memory map (bytes)
+constexpr int WA_Q_BYTES = 256 * 64;  // 2 row tiles x 128 rows x 32 dims
+constexpr int WA_K_BYTES = 160 * 64;
+constexpr int WA_V_BYTES = 160 * 64;
+constexpr int WA_QKV_BYTES = WA_Q_BYTES + WA_K_BYTES + WA_V_BYTES;  // 36864 per buffer
+constexpr int WA_P_TILE_BYTES = 128 * WA_KEYS * 2;                  // 40960 per row tile
+constexpr int WA_BIAS_BYTES = ((WA_N * WA_BIAS_PITCH * 2 + 127) / 128) * 128;
+constexpr int WA_OFF_QKV = 0;
+constexpr int WA_OFF_P = 2 * WA_QKV_BYTES;
+constexpr int WA_OFF_BIAS = WA_OFF_P + 2 * WA_P_TILE_BYTES;
+// token / region tables are a 4-deep ring (slot = item & 3): the q loader refills a slot as soon as S(item - 2) has been
+// issued, while the softmax warps of item - 2 are still reading theirs
+constexpr int WA_RING = 4;
+constexpr int WA_OFF_TOK = WA_OFF_BIAS + WA_BIAS_BYTES;         // int [3 loaders][WA_RING][160]
+constexpr int WA_OFF_RID = WA_OFF_TOK + 3 * WA_RING * 160 * 4;  // uint8 [WA_RING][160]
+constexpr int WA_OFF_XCHG = WA_OFF_RID + WA_RING * 160;         // float [2 kinds][2 halves][160 rows]
+constexpr int WA_OFF_BAR = WA_OFF_XCHG + 2 * 2 * 160 * 4;       // mbarriers + tmem slot
+constexpr int WA_SMEM = WA_OFF_BAR + 128 + 128 /*align slack*/;
+
+// TMEM columns
+constexpr int WA_TM_S0 = 0, WA_TM_S1 = 160, WA_TM_O0 = 320, WA_TM_O1 = 352, WA_TM_COLS = 512;
+
+// UMMA shared-memory descriptor without swizzle: operands live as 8-row x 16-byte "core matrices" (128 contiguous
+// bytes); lbo / sbo are the byte distances between core matrices (K-major: lbo along K, sbo along M/N;
+// MN-major: sbo along M/N, lbo along K).
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
+  return d;                             // layout type 0 = no swizzle
 }
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                               uint32_t b0, uint32_t b1) {
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-      "{%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
 }
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// byte offset of the 16-byte chunk (row, chunk) inside an operand stored as core matrices with `cores_per_group` cores
+// along the contiguous (K for q/k/P, dims for v) direction
+__device__ __forceinline__ uint32_t core_off(int row, int chunk, int cores_per_group) {
+  return static_cast<uint32_t>(((row >> 3) * cores_per_group + chunk) * 128 + (row & 7) * 16);
+}
 
-__global__ void __launch_bounds__(WA_THREADS, 2)
+__global__ void __launch_bounds__(WA_THREADS, 1)
 window_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const bf16* __restrict__ bias_dense,
-                        StageGeom g, int n_seg, int C, float scale_log2e) {
-  extern __shared__ __align__(16) uint8_t wa_smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(wa_smem);
-  bf16* sK = sQ + WA_ROWS * WA_PITCH;
-  bf16* sV = sK + WA_ROWS * WA_PITCH;
-  bf16* sBias = sV + WA_ROWS * WA_PITCH;
-  int* sTok = reinterpret_cast<int*>(sBias + WA_N * WA_BIAS_PITCH);
-  uint8_t* sRid = reinterpret_cast<uint8_t*>(sTok + WA_ROWS);
+                        StageGeom g, int n_seg, int C, int n_heads, float scale_log2e) {
+  // NOTE: pointers must stay derived from the __shared__ array itself (no integer round trip), otherwise the compiler
+  // falls back to generic LD/ST for every shared-memory access
+  extern __shared__ __align__(128) uint8_t smem[];
+  const bf16* sBias = reinterpret_cast<const bf16*>(smem + WA_OFF_BIAS);
+  int* sTok = reinterpret_cast<int*>(smem + WA_OFF_TOK);
+  uint8_t* sRid = smem + WA_OFF_RID;
+  float* sX = reinterpret_cast<float*>(smem + WA_OFF_XCHG);
+  uint64_t* bar_qk_full = reinterpret_cast<uint64_t*>(smem + WA_OFF_BAR);  // [2]
+  uint64_t* bar_qk_empty = bar_qk_full + 2;                                // [2]
+  uint64_t* bar_v_full = bar_qk_empty + 2;                                 // [2]
+  uint64_t* bar_v_empty = bar_v_full + 2;                                  // [2]
+  uint64_t* bar_s_full = bar_v_empty + 2;
+  uint64_t* bar_p_full = bar_s_full + 1;
+  uint64_t* bar_o_full = bar_p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int gq = lane >> 2, tq = lane & 3;
-  const int head = blockIdx.y;
   const int nwin = windows_per_segment(g);
   const int T = g.D * g.H * g.W;
   const int n_items = n_seg * nwin;
   const bool shifted = (g.sd | g.sh | g.sw) != 0;
-  const float MASK_L2 = -100.0f * 1.4426950408889634f;
+  // work units are (head, segment, window) triples in head-major order; every CTA takes one contiguous, equally sized
+  // range, so a CTA changes head (and reloads the 44 KB bias table) at most ceil(heads / CTAs) + 1 times
+  const long long n_units = static_cast<long long>(n_heads) * n_items;
+  const int u_lo = static_cast<int>(n_units * blockIdx.x / gridDim.x);
+  const int u_hi = static_cast<int>(n_units * (blockIdx.x + 1) / gridDim.x);
+  const int n_my = u_hi - u_lo;
 
-  // one-time: zero q/k/v staging (pad rows stay zero forever), load this head's bias
-  for (int i = tid; i < 3 * WA_ROWS * WA_PITCH / 8; i += WA_THREADS) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(bias_dense + static_cast<size_t>(head) * WA_N * WA_BIAS_PITCH);
-    for (int i = tid; i < WA_N * WA_BIAS_PITCH / 8; i += WA_THREADS) reinterpret_cast<uint4*>(sBias)[i] = __ldg(src + i);
+  // ---- one-time setup: zero the q/k/v staging (pad rows stay zero forever), load this head's bias, barriers, TMEM
+  for (int i = tid; i < 2 * WA_QKV_BYTES / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem + WA_OFF_QKV)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * WA_P_TILE_BYTES / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem + WA_OFF_P)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 11 && lane == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_qk_full[b], 2);  // the q loader and the k loader
+      mbar_init(&bar_qk_empty[b], 1);
+      mbar_init(&bar_v_full[b], 1);
+      mbar_init(&bar_v_empty[b], 1);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_p_full, 10);
+    mbar_init(bar_o_full, 1);
+    fence_barrier_init();
   }
-  for (int i = tid; i < WA_ROWS; i += WA_THREADS) { sTok[i] = 0; sRid[i] = 0; }
+  if (warp == 10) tmem_alloc(tmem_slot, WA_TM_COLS);
+  fence_proxy_async_smem();  // the zero fill above must be visible to the tensor core's operand reads
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int seg = item / nwin, win = item - seg * nwin;
-    __syncthreads();  // previous item fully consumed (and the one-time init is visible)
-    if (tid < WA_N) {
-      sTok[tid] = window_source_token(g, win, tid);
-      sRid[tid] = static_cast<uint8_t>(shifted ? shift_region_id(g, win, tid) : 0);
-    }
-    __syncthreads();
-    {
-      const bf16* base = qkv + static_cast<size_t>(seg) * T * 3 * C + head * 32;
-      for (int c = tid; c < WA_N * 12; c += WA_THREADS) {
-        const int r = c / 12, rem = c - r * 12, part = rem >> 2, ch = rem & 3;
-        const bf16* src = base + static_cast<size_t>(sTok[r]) * 3 * C + part * C + ch * 8;
-        cp_async_16(sQ + (part * WA_ROWS + r) * WA_PITCH + ch * 8, src);
-      }
-      cp_async_wait_all();
-    }
-    __syncthreads();
-
-    // does this window straddle the wrap line? (otherwise every region id is equal and the mask is all zero)
-    bool need_mask = false;
-    if (shifted) {
-      const int nw = g.W / g.ww, nh = g.H / g.wh;
-      need_mask = ((win % nw) == nw - 1 && g.sw) || (((win / nw) % nh) == nh - 1 && g.sh);
-    }
-
-    for (int stripe = warp; stripe < WA_ROWS / 16; stripe += WA_WARPS) {
-      const int r0 = stripe * 16;
-      // ---- Q fragments (2 k-steps of 16 dims)
-      uint32_t qa[2][4];
-      {
-        const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int col = (lane >> 4) * 8;
-        ldmatrix_x4(qa[0][0], qa[0][1], qa[0][2], qa[0][3], sQ + row * WA_PITCH + col);
-        ldmatrix_x4(qa[1][0], qa[1][1], qa[1][2], qa[1][3], sQ + row * WA_PITCH + 16 + col);
-      }
-      // ---- S = Q K^T
-      float s[WA_KTILES][4];
-#pragma unroll
-      for (int j = 0; j < WA_KTILES; ++j) {
-        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        uint32_t b0, b1, b2, b3;
-        ldmatrix_x4(b0, b1, b2, b3, sK + (8 * j + (lane & 7)) * WA_PITCH + (lane >> 3) * 8);
-        mma_bf16_16816(s[j], qa[0][0], qa[0][1], qa[0][2], qa[0][3], b0, b1);
-        mma_bf16_16816(s[j], qa[1][0], qa[1][1], qa[1][2], qa[1][3], b2, b3);
-      }
-      // ---- scale, + bias, + mask (log2 domain), row max
-      const int row_a = r0 + gq, row_b = r0 + gq + 8;
-      const int brow_a = min(row_a, WA_N - 1), brow_b = min(row_b, WA_N - 1);
-      const int rid_a = sRid[brow_a], rid_b = sRid[brow_b];
-      float mx_a = -INFINITY, mx_b = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < WA_KTILES; ++j) {
-        const int col = 8 * j + 2 * tq;
-        const float2 ba = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sBias + brow_a * WA_BIAS_PITCH + col));
-        const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sBias + brow_b * WA_BIAS_PITCH + col));
-        s[j][0] = fmaf(s[j][0], scale_log2e, ba.x);
-        s[j][1] = fmaf(s[j][1], scale_log2e, ba.y);
-        s[j][2] = fmaf(s[j][2], scale_log2e, bb.x);
-        s[j][3] = fmaf(s[j][3], scale_log2e, bb.y);
-        if (need_mask) {
-          const int c0 = sRid[min(col, WA_N - 1)], c1 = sRid[min(col + 1, WA_N - 1)];
-          if (c0 != rid_a) s[j][0] += MASK_L2;
-          if (c1 != rid_a) s[j][1] += MASK_L2;
-          if (c0 != rid_b) s[j][2] += MASK_L2;
-          if (c1 != rid_b) s[j][3] += MASK_L2;
-        }
-        if (j == WA_KTILES - 1) {  // key columns 147..151 do not exist
-          if (col >= WA_N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-          if (col + 1 >= WA_N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
-        }
-        mx_a = fmaxf(mx_a, fmaxf(s[j][0], s[j][1]));
-        mx_b = fmaxf(mx_b, fmaxf(s[j][2], s[j][3]));
-      }
-      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
-      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
-      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
-      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
-      // ---- P = exp2(S - max), row sums
-      float sum_a = 0.f, sum_b = 0.f;
-#pragma unroll
-      for (int j = 0; j < WA_KTILES; ++j) {
-        s[j][0] = exp2f(s[j][0] - mx_a);
-        s[j][1] = exp2f(s[j][1] - mx_a);
-        s[j][2] = exp2f(s[j][2] - mx_b);
-        s[j][3] = exp2f(s[j][3] - mx_b);
-        sum_a += s[j][0] + s[j][1];
-        sum_b += s[j][2] + s[j][3];
-      }
-      sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 1);
-      sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 2);
-      sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 1);
-      sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 2);
-      // ---- O = P V  (P taken from the accumulator registers as the A operand)
-      float o[4][4];
-#pragma unroll
-      for (int nn = 0; nn < 4; ++nn) o[nn][0] = o[nn][1] = o[nn][2] = o[nn][3] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < (WA_KTILES + 1) / 2; ++kk) {
-        const uint32_t a0 = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-        const uint32_t a1 = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-        uint32_t a2 = 0u, a3 = 0u;
-        if (2 * kk + 1 < WA_KTILES) {
-          a2 = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-          a3 = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        }
-        const int vrow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int vcol = (lane >> 4) * 8;
-        uint32_t b0, b1, b2, b3;
-        ldmatrix_x4_trans(b0, b1, b2, b3, sV + vrow * WA_PITCH + vcol);
-        mma_bf16_16816(o[0], a0, a1, a2, a3, b0, b1);
-        mma_bf16_16816(o[1], a0, a1, a2, a3, b2, b3);
-        ldmatrix_x4_trans(b0, b1, b2, b3, sV + vrow * WA_PITCH + 16 + vcol);
-        mma_bf16_16816(o[2], a0, a1, a2, a3, b0, b1);
-        mma_bf16_16816(o[3], a0, a1, a2, a3, b2, b3);
-      }
-      // ---- normalise, stage the stripe's 16 x 32 output in this warp's (now dead) Q rows, scatter 64-byte rows
-      const float inv_a = 1.0f / sum_a, inv_b = 1.0f / sum_b;
-      __syncwarp();
-#pragma unroll
-      for (int nn = 0; nn < 4; ++nn) {
-        *reinterpret_cast<uint32_t*>(sQ + row_a * WA_PITCH + nn * 8 + 2 * tq) = pack_bf16x2(o[nn][0] * inv_a, o[nn][1] * inv_a);
-        *reinterpret_cast<uint32_t*>(sQ + row_b * WA_PITCH + nn * 8 + 2 * tq) = pack_bf16x2(o[nn][2] * inv_b, o[nn][3] * inv_b);
+  if (warp == 9 || warp == 10 || warp == 13) {
+    // ===================================================================== loaders: warp 9 -> q, 10 -> k, 13 -> v
+    const int part = (warp == 9) ? 0 : (warp == 10 ? 1 : 2);
+    int* myTok = sTok + part * WA_RING * 160;
+    uint64_t* full = (part == 2) ? bar_v_full : bar_qk_full;
+    uint64_t* empty = (part == 2) ? bar_v_empty : bar_qk_empty;
+    const uint32_t part_off = (part == 0) ? 0u : (part == 1 ? static_cast<uint32_t>(WA_Q_BYTES) : static_cast<uint32_t>(WA_Q_BYTES + WA_K_BYTES));
+    const int sub = lane >> 2, ch = lane & 3;  // 4 lanes fetch the 64 contiguous bytes of one row
+    for (int j = 0; j < n_my; ++j) {
+      const int buf = j & 1, slot = j & (WA_RING - 1);
+      const int unit = u_lo + j;
+      const int head = unit / n_items, item = unit - head * n_items;
+      const int seg = item / nwin, win = item - seg * nwin;
+      mbar_wait(&empty[buf], ((j >> 1) & 1) ^ 1);
+      for (int r = lane; r < WA_N; r += 32) {
+        myTok[slot * 160 + r] = window_source_token(g, win, r);
+        if (part == 0) sRid[slot * 160 + r] = static_cast<uint8_t>(shifted ? shift_region_id(g, win, r) : 0);
       }
       __syncwarp();
+      const bf16* base = qkv + static_cast<size_t>(seg) * T * 3 * C + part * C + head * 32 + ch * 8;
+      const uint32_t sbuf = smem_u32(smem + WA_OFF_QKV + buf * WA_QKV_BYTES) + part_off;
+#pragma unroll 4
+      for (int r = sub; r < WA_N; r += 8)
+        cp_async_16(sbuf + core_off(r, ch, 4), base + static_cast<size_t>(myTok[slot * 160 + r]) * 3 * C);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[buf]);
+    }
+  } else if (warp == 11) {
+    // ===================================================================== MMA issuer
+    if (lane == 0 && n_my > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_KEYS);               // A, B K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);       // B (= v) MN-major
+      auto issue_s = [&](int j) {
+        const uint32_t b = smem_u32(smem + WA_OFF_QKV + (j & 1) * WA_QKV_BYTES);
+        const uint32_t q_addr = b, k_addr = b + WA_Q_BYTES;
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int row = r0 + h2 * 8 + (lane >> 2);
-        if (row < WA_N) {
-          const uint4 v = *reinterpret_cast<const uint4*>(sQ + row * WA_PITCH + (lane & 3) * 8);
-          bf16* dst = out + (static_cast<size_t>(seg) * T + sTok[row]) * C + head * 32 + (lane & 3) * 8;
-          *reinterpret_cast<uint4*>(dst) = v;
+        for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_bf16_ss(tmem_base + (tile ? WA_TM_S1 : WA_TM_S0),
+                         umma_desc_nosw(q_addr + tile * (16 * 512) + kk * 256, 128, 512),
+                         umma_desc_nosw(k_addr + kk * 256, 128, 512), idesc_s, kk);
+        umma_commit(bar_s_full);
+      };
+      mbar_wait(&bar_qk_full[0], 0);
+      tcgen05_fence_after();
+      issue_s(0);
+      umma_commit(&bar_qk_empty[0]);
+      for (int j = 0; j < n_my; ++j) {
+        mbar_wait(bar_p_full, j & 1);  // softmax(j) done: S buffer free, P(j) in smem, O(j-1) drained
+        tcgen05_fence_after();
+        if (j + 1 < n_my) {
+          mbar_wait(&bar_qk_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tcgen05_fence_after();
+          issue_s(j + 1);
+          umma_commit(&bar_qk_empty[(j + 1) & 1]);
         }
+        mbar_wait(&bar_v_full[j & 1], (j >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t v_addr = smem_u32(smem + WA_OFF_QKV + (j & 1) * WA_QKV_BYTES) + WA_Q_BYTES + WA_K_BYTES;
+        const uint32_t p_addr = smem_u32(smem + WA_OFF_P);
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+          for (int kk = 0; kk < WA_KEYS / 16; ++kk)
+            umma_bf16_ss(tmem_base + (tile ? WA_TM_O1 : WA_TM_O0),
+                         umma_desc_nosw(p_addr + tile * WA_P_TILE_BYTES + kk * 256, 128, (WA_KEYS / 8) * 128),
+                         umma_desc_nosw(v_addr + kk * 1024, /*lbo: key groups*/ 512, /*sbo: dim groups*/ 128), idesc_o, kk);
+        umma_commit(bar_o_full);
+        umma_commit(&bar_v_empty[j & 1]);
       }
     }
+  } else {
+    // ===================================================================== softmax + epilogue (warps 0-8, 12)
+    const int tile = (warp >= 8) ? 1 : 0;
+    const int q = warp & 3;                              // TMEM lane quarter
+    const int half = (warp >= 8) ? (warp == 12) : (warp >> 2);
+    const int row = tile * 128 + q * 32 + lane;          // query row inside the window
+    const int brow = min(row, WA_N - 1);
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int pair_bar = 1 + tile * 4 + q;               // named barrier shared with the warp owning the other columns
+    const float MASK_L2 = -100.0f * 1.4426950408889634f;
+    const int col0 = half * 80;
+    float inv_prev = 0.f;
+    int tok_prev = 0, seg_prev = 0, head_prev = 0, head_loaded = -1;
+    const int st = (warp < 9) ? tid : (tid - 96);  // index among the 320 softmax threads (warps 0-8 and 12)
+
+    auto store_o = [&](float inv, int seg, int tok, int head, bool valid) {
+      uint32_t acc[16];
+      tmem_ld_32x16(tmem_base + lane_addr + (tile ? WA_TM_O1 : WA_TM_O0) + half * 16, acc);
+      tmem_ld_wait();
+      if (valid) {
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(__uint_as_float(acc[0]) * inv, __uint_as_float(acc[1]) * inv);
+        o0.y = pack_bf16x2(__uint_as_float(acc[2]) * inv, __uint_as_float(acc[3]) * inv);
+        o0.z = pack_bf16x2(__uint_as_float(acc[4]) * inv, __uint_as_float(acc[5]) * inv);
+        o0.w = pack_bf16x2(__uint_as_float(acc[6]) * inv, __uint_as_float(acc[7]) * inv);
+        o1.x = pack_bf16x2(__uint_as_float(acc[8]) * inv, __uint_as_float(acc[9]) * inv);
+        o1.y = pack_bf16x2(__uint_as_float(acc[10]) * inv, __uint_as_float(acc[11]) * inv);
+        o1.z = pack_bf16x2(__uint_as_float(acc[12]) * inv, __uint_as_float(acc[13]) * inv);
+        o1.w = pack_bf16x2(__uint_as_float(acc[14]) * inv, __uint_as_float(acc[15]) * inv);
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(seg) * T + tok) * C + head * 32 + half * 16);
+        dst[0] = o0;
+        dst[1] = o1;
+      }
+    };
+
+    for (int j = 0; j < n_my; ++j) {
+      const int slot = j & (WA_RING - 1);
+      const int unit = u_lo + j;
+      const int head = unit / n_items, item = unit - head * n_items;
+      const int seg = item / nwin, win = item - seg * nwin;
+      if (head != head_loaded) {  // (re)load this head's dense bias; uniform across the softmax warps
+        asm volatile("bar.sync 7, 320;" ::: "memory");
+        const uint4* src = reinterpret_cast<const uint4*>(bias_dense + static_cast<size_t>(head) * WA_N * WA_BIAS_PITCH);
+        uint4* dst = reinterpret_cast<uint4*>(smem + WA_OFF_BIAS);
+        for (int i = st; i < WA_N * WA_BIAS_PITCH / 8; i += 320) dst[i] = __ldg(src + i);
+        asm volatile("bar.sync 7, 320;" ::: "memory");
+        head_loaded = head;
+      }
+      bool need_mask = false;
+      if (shifted) {
+        const int nw = g.W / g.ww, nh = g.H / g.wh;
+        need_mask = ((win % nw) == nw - 1 && g.sw) || (((win / nw) % nh) == nh - 1 && g.sh);
+      }
+      mbar_wait(bar_s_full, j & 1);
+      tcgen05_fence_after();
+      const int tok = sTok[slot * 160 + brow];
+      const int rid = sRid[slot * 160 + brow];
+      // ---- pass 1: t = s * scale * log2e + bias (+ mask), running max; 80 columns per thread kept in registers
+      float t[80];
+      float mx = -INFINITY;
+      const uint32_t s_addr = tmem_base + lane_addr + (tile ? WA_TM_S1 : WA_TM_S0) + col0;
+#pragma unroll
+      for (int c = 0; c < 80; c += 16) {
+        uint32_t acc[16];
+        tmem_ld_32x16(s_addr + c, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          const int col = col0 + c + i;  // 8 consecutive key columns
+          if (col < WA_BIAS_PITCH) {     // compile-time after unrolling except for `half`
+            const uint4 b4 = *reinterpret_cast<const uint4*>(sBias + brow * WA_BIAS_PITCH + col);
+            const float2 b01 = unpack_bf16x2(b4.x), b23 = unpack_bf16x2(b4.y), b45 = unpack_bf16x2(b4.z), b67 = unpack_bf16x2(b4.w);
+            const float bb[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = fmaf(__uint_as_float(acc[i + e]), scale_log2e, bb[e]);
+              if (need_mask && sRid[slot * 160 + min(col + e, WA_N - 1)] != rid) v += MASK_L2;
+              if (col + e >= WA_N) v = -INFINITY;
+              t[c + i + e] = v;
+              mx = fmaxf(mx, v);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[c + i + e] = -INFINITY;
+          }
+        }
+      }
+      tcgen05_fence_before();  // all TMEM reads of S(j) are complete (wait::ld above)
+      sX[(0 * 2 + half) * 160 + row] = mx;  // rows of tile 1 are stored at 32 + (row - 128)
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, sX[(0 * 2 + (half ^ 1)) * 160 + row]);
+      // ---- epilogue of the previous item (its P v finished long ago); also frees the P buffer for this item
+      if (j > 0) {
+        mbar_wait(bar_o_full, (j - 1) & 1);
+        tcgen05_fence_after();
+        store_o(inv_prev, seg_prev, tok_prev, head_prev, row < WA_N);
+        tcgen05_fence_before();
+      }
+      // ---- pass 2: p = exp2(t - max) -> bf16 A-operand tile, row sum
+      float sum = 0.f;
+      uint8_t* p_row = smem + WA_OFF_P + tile * WA_P_TILE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 80; c += 8) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          p[e] = ex2_approx(t[c + e] - mx);
+          sum += p[e];
+        }
+        uint4 u;
+        u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
+        u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(p_row + core_off(q * 32 + lane, (col0 + c) >> 3, WA_KEYS / 8)) = u;
+      }
+      sX[(1 * 2 + half) * 160 + row] = sum;
+      fence_proxy_async_smem();  // P writes -> visible to the tensor core
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      sum += sX[(1 * 2 + (half ^ 1)) * 160 + row];
+      inv_prev = 1.0f / sum;
+      tok_prev = tok;
+      seg_prev = seg;
+      head_prev = head;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full);
+    }
+    if (n_my > 0) {
+      mbar_wait(bar_o_full, (n_my - 1) & 1);
+      tcgen05_fence_after();
+      store_o(inv_prev, seg_prev, tok_prev, head_prev, row < WA_N);
+      tcgen05_fence_before();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, WA_TM_COLS);
   }
 }
 
@@ -264,15 +405,13 @@ extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void
     }
     configured = true;
   }
-  const int n_items = n_seg * windows_per_segment(g);
-  int groups = (2 * sm_count() + n_heads - 1) / n_heads;
-  if (groups > n_items) groups = n_items;
-  if (groups < 1) groups = 1;
-  dim3 grid(groups, n_heads);
+  const long long n_units = static_cast<long long>(n_seg) * windows_per_segment(g) * n_heads;
+  int grid = sm_count();  // one persistent CTA per SM (it owns all 512 TMEM columns)
+  if (grid > n_units) grid = static_cast<int>(n_units);
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
   window_attention_kernel<<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g,
-      n_seg, C, scale_log2e);
+      n_seg, C, n_heads, scale_log2e);
   return check_launch("window_attention_kernel");
 }
 

@@ -1,0 +1,88 @@
+"""GPU probe: launch every distinct (kernel, shape) of the config-2 forward (B=32 clips -> 96 segments) exactly once, in a
+fixed printed order, so that one `ncu --set full` capture of this script holds one record per hot-path kernel shape.
+
+    python tools/gpu_kernel_zoo.py [gemm|attn|rows|enc|all]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import lrce_b200  # noqa: F401
+from lrce_b200 import ops
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev = "cuda"
+torch.manual_seed(0)
+N_SEG = 96
+order = []
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).bfloat16()
+
+
+def gemm(tag, M, N, K, epi):
+    a, w = rnd(M, K, scale=0.5), rnd(N, K, scale=0.05)
+    bias = torch.randn(N, device=dev)
+    res = rnd(M, N) if epi == ops.EPI_BIAS_RESIDUAL else None
+    ln = (torch.ones(N, device=dev), torch.zeros(N, device=dev), 1e-5) if epi == ops.EPI_BIAS_LN else None
+    torch.cuda.synchronize()
+    ops.gemm(a, w, bias, epilogue=epi, residual=res, ln=ln)
+    torch.cuda.synchronize()
+    order.append(f"gemm {tag} M{M} N{N} K{K} epi{epi}")
+
+
+if which in ("gemm", "all"):
+    gemm("patch-embed", 903168, 128, 96, ops.EPI_BIAS_LN)
+    for st, (M, C) in enumerate([(903168, 128), (225792, 256), (56448, 512), (14112, 1024)], 1):
+        gemm(f"s{st}.qkv", M, 3 * C, C, ops.EPI_BIAS)
+        gemm(f"s{st}.proj", M, C, C, ops.EPI_BIAS_RESIDUAL)
+        gemm(f"s{st}.fc1", M, 4 * C, C, ops.EPI_BIAS_GELU)
+        gemm(f"s{st}.fc2", M, C, 4 * C, ops.EPI_BIAS_RESIDUAL)
+        if st < 4:
+            gemm(f"merge{st}", M // 4, 2 * C, 4 * C, ops.EPI_BIAS)
+    gemm("video-proj", 14112, 768, 1024, ops.EPI_BIAS)
+    gemm("enc-kv", 14400, 18432, 768, ops.EPI_BIAS)
+
+if which in ("attn", "all"):
+    for name, hw, C, heads in [("s1", 56, 128, 4), ("s2", 28, 256, 8), ("s3", 14, 512, 16), ("s4", 7, 1024, 32)]:
+        T = 3 * hw * hw
+        qkv = rnd(N_SEG * T, 3 * C)
+        bias = ops.window_bias_pack(torch.randn(2535, heads, device=dev) * 0.5)
+        for shift in ((0, 0), (3, 3)) if hw > 7 else ((0, 0),):
+            torch.cuda.synchronize()
+            ops.window_attention(qkv, bias, N_SEG, 3, hw, hw, C, heads, shift)
+            torch.cuda.synchronize()
+            order.append(f"attn {name} shift{shift}")
+
+if which in ("rows", "all"):
+    clips = torch.rand(N_SEG, 5, 3, 224, 224, device=dev)
+    ops.patch_gather(clips)
+    order.append("patch_gather")
+    for M, C in [(903168, 128), (225792, 256), (56448, 512), (14112, 1024)]:
+        x = rnd(M, C)
+        g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        ops.layernorm(x, g, b, 1e-5)
+        order.append(f"layernorm M{M} C{C}")
+    for hw, C in [(56, 128), (28, 256), (14, 512)]:
+        x = rnd(N_SEG * 3 * hw * hw, C)
+        g, b = torch.ones(4 * C, device=dev), torch.zeros(4 * C, device=dev)
+        ops.patch_merge_ln(x, g, b, 1e-5, N_SEG, 3, hw, hw, C)
+        order.append(f"patch_merge_ln C{C}")
+
+if which in ("enc", "all"):
+    os.environ["LRCE_B200_NO_GRAPH"] = "1"
+    from lrce_b200 import fusion
+
+    fusion._NO_GRAPH = True
+    m = lrce_b200.LRCEOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [1], 32).cuda().eval()  # S=1: one recurrent step
+    vf = rnd(32, 1, 3, 49, 1024)
+    tf = torch.randn(32, 32, 768, device=dev)
+    with torch.no_grad():
+        m(vf, tf)
+    torch.cuda.synchronize()
+    order.append("encoder S=1 forward (12 layer-steps, kernel by kernel)")
+
+print("\n".join(order))

@@ -72,6 +72,59 @@ def test_window_remap_tensor_bit_exact(ops, name, C):
         assert torch.equal(back, x)  # window_reverse + roll(+shift) is the exact inverse
 
 
+def chunk_stats(x):
+    """torch statement of the LayerNorm partials a producing GEMM emits: (M, C) bf16 -> fp32 [C/64, M, 2] = (mean, M2)"""
+    M, C = x.shape
+    v = x.float().view(M, C // 64, 64)
+    mean = v.mean(-1)
+    m2 = ((v - mean[..., None]) ** 2).sum(-1)
+    return torch.stack([mean, m2], -1).permute(1, 0, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM: epilogues, LayerNorm folding, row-statistics emission
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(300, 384, 128), (1000, 1536, 512), (4097, 256, 1024)])
+@pytest.mark.parametrize("epi", ["bias", "gelu"])
+def test_gemm_layernorm_folded_input(ops, M, N, K, epi):
+    """out = act(LayerNorm(x) W^T + b) with the normalisation folded into the GEMM epilogue == the two-step torch result"""
+    x = (seeded((M, K), 1, 2.0) + 0.7).bfloat16().cuda()  # non-zero row mean: exercises the mean * colsum cancellation
+    w, b = seeded((N, K), 2, 0.05).cuda(), seeded((N,), 3).cuda()
+    g, beta = (1 + 0.2 * seeded((K,), 4)).cuda(), (0.2 * seeded((K,), 5)).cuda()
+    ref = torch.nn.functional.layer_norm(x.float(), (K,), g, beta, 1e-5) @ w.t() + b
+    if epi == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    wg = (w.double() * g.double()[None]).bfloat16()
+    colsum = wg.double().sum(1).float()
+    bias = (b.double() + w.double() @ beta.double()).float()
+    y = ops.gemm(x, wg, bias, epilogue=ops.EPI_BIAS_GELU if epi == "gelu" else ops.EPI_BIAS,
+                 ln_in=(chunk_stats(x), colsum, 1e-5))
+    assert rel_l2(y, ref) < 6e-3, rel_l2(y, ref)  # bf16 weights + bf16 output rounding
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(300, 128, 128, "res"), (1000, 512, 2048, "res"), (1500, 256, 512, "bias"),
+                                       (700, 128, 96, "ln")])
+def test_gemm_emits_row_statistics(ops, M, N, K, epi):
+    a, w, b = seeded((M, K), 6, 0.5).bfloat16().cuda(), seeded((N, K), 7, 0.05).bfloat16().cuda(), seeded((N,), 8).cuda()
+    st = torch.zeros(N // 64 * M * 2, device="cuda")
+    if epi == "res":
+        r = seeded((M, N), 9).bfloat16().cuda()
+        y = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_RESIDUAL, residual=r, stats_out=st)
+        ref = a.float() @ w.float().t() + b + r.float()
+    elif epi == "ln":
+        g, beta = (1 + 0.2 * seeded((N,), 4)).cuda(), (0.2 * seeded((N,), 5)).cuda()
+        y = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_LN, ln=(g, beta, 1e-5), stats_out=st)
+        ref = torch.nn.functional.layer_norm(a.float() @ w.float().t() + b, (N,), g, beta, 1e-5)
+    else:
+        y = ops.gemm(a, w, b, stats_out=st)
+        ref = a.float() @ w.float().t() + b
+    assert rel_l2(y, ref) < 6e-3
+    want = chunk_stats(y)  # the kernel takes them just before the bf16 rounding of y: equal up to the rounding noise
+    got = st.view(N // 64, M, 2)
+    assert (got[..., 0] - want[..., 0]).abs().max().item() < 2e-3 * max(1.0, y.float().abs().max().item())
+    assert ((got[..., 1] - want[..., 1]).abs() / want[..., 1].clamp_min(1e-3)).max().item() < 2e-2
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # row kernels
 # ------------------------------------------------------------------------------------------------------------------
@@ -180,12 +233,11 @@ def test_swin_block_vs_reference_golden(ops, golden, swin_cuda, tag, layer, blk,
     x0 = seeded((1, 3, hw, hw, dim), 100 + layer * 10 + blk)
     x = x0.bfloat16().cuda().view(-1, dim).clone()
     shift = (3, 3) if (blk % 2 and hw > 7) else (0, 0)
-    xn = ops.layernorm(x, pk["n1g"], pk["n1b"], 1e-5)
-    qkv = ops.gemm(xn, pk["wqkv"], pk["bqkv"])
+    st_a, st_b = chunk_stats(x), torch.empty(dim // 64 * x.shape[0] * 2, device="cuda")
+    qkv = ops.gemm(x, pk["wqkv"], pk["bqkv"], ln_in=(st_a, pk["cqkv"], 1e-5))
     att = ops.window_attention(qkv, pk["bias"], 1, 3, hw, hw, dim, heads, shift)
-    ops.gemm(att, pk["wproj"], pk["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x)
-    xn = ops.layernorm(x, pk["n2g"], pk["n2b"], 1e-5)
-    hid = ops.gemm(xn, pk["w1"], pk["b1"], epilogue=ops.EPI_BIAS_GELU)
+    ops.gemm(att, pk["wproj"], pk["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_b)
+    hid = ops.gemm(x, pk["w1"], pk["b1"], epilogue=ops.EPI_BIAS_GELU, ln_in=(st_b, pk["c1"], 1e-5))
     ops.gemm(hid, pk["w2"], pk["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x)
     ref = torch.from_numpy(golden["swin_modules"][f"{tag}.out"])
     got = x.float().cpu().view(1, 3, hw, hw, dim)

@@ -38,19 +38,24 @@ def check(M, N, K, epi, fp32=False):
     return ok
 
 
-def bench(M, N, K, epi, iters=20):
+def bench(M, N, K, epi, iters=20, lnin=False, stats=False):
     a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     bias = torch.randn(N, device=dev)
     res = torch.randn(M, N, device=dev).bfloat16() if epi == ops.EPI_BIAS_RESIDUAL else None
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    kw = {}
+    if lnin:
+        kw["ln_in"] = (torch.rand(K // 64 * M * 2, device=dev) + 0.5, torch.randn(N, device=dev), 1e-5)
+    if stats:
+        kw["stats_out"] = torch.empty(N // 64 * M * 2, device=dev)
     for _ in range(3):
-        ops.gemm(a, w, bias, epilogue=epi, residual=res, out=out)
+        ops.gemm(a, w, bias, epilogue=epi, residual=res, out=out, **kw)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(iters):
-        ops.gemm(a, w, bias, epilogue=epi, residual=res, out=out)
+        ops.gemm(a, w, bias, epilogue=epi, residual=res, out=out, **kw)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     tf = 2.0 * M * N * K / ms / 1e9
@@ -62,7 +67,7 @@ def bench(M, N, K, epi, iters=20):
         torch.matmul(a, w.t())
     e1.record(); torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / iters
-    print(f"BENCH M={M} N={N} K={K} epi={epi}: {ms*1e3:.1f} us  {tf:.1f} TFLOP/s  (cuBLAS matmul {ms2*1e3:.1f} us {2.0*M*N*K/ms2/1e9:.1f} TF)", flush=True)
+    print(f"BENCH M={M} N={N} K={K} epi={epi} lnin={int(lnin)} stats={int(stats)}: {ms*1e3:.1f} us  {tf:.1f} TFLOP/s  (cuBLAS matmul {ms2*1e3:.1f} us {2.0*M*N*K/ms2/1e9:.1f} TF)", flush=True)
 
 
 if __name__ == "__main__":
@@ -84,6 +89,11 @@ if __name__ == "__main__":
     print("ALL_OK" if ok else "SOME_FAIL", flush=True)
     if ok or "--force-bench" in sys.argv:
         bench(8192, 8192, 8192, ops.EPI_BIAS)
+        for M, C in ((903168, 128), (225792, 256), (56448, 512), (14112, 1024)):  # one Swin block per stage, as executed
+            bench(M, 3 * C, C, ops.EPI_BIAS, lnin=True)
+            bench(M, C, C, ops.EPI_BIAS_RESIDUAL, stats=True)
+            bench(M, 4 * C, C, ops.EPI_BIAS_GELU, lnin=True)
+            bench(M, C, 4 * C, ops.EPI_BIAS_RESIDUAL, stats=True)
         bench(56448, 1536, 512, ops.EPI_BIAS)
         bench(56448, 2048, 512, ops.EPI_BIAS_GELU)
         bench(56448, 512, 2048, ops.EPI_BIAS_RESIDUAL)

@@ -15,7 +15,8 @@ from lrce_b200 import ops
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 dev = "cuda"
 torch.manual_seed(0)
-N_SEG = 96
+N_SEG = int(os.environ.get("ZOO_SEG", "96"))  # use ZOO_SEG=24 under `ncu --set full` (replays save/restore every buffer)
+SC = N_SEG / 96.0
 order = []
 
 
@@ -23,28 +24,46 @@ def rnd(*shape, scale=1.0):
     return (torch.randn(*shape, device=dev) * scale).bfloat16()
 
 
-def gemm(tag, M, N, K, epi):
+def gemm(tag, M, N, K, epi, lnin=False, stats=False):
+    M = int(M * SC)
     a, w = rnd(M, K, scale=0.5), rnd(N, K, scale=0.05)
     bias = torch.randn(N, device=dev)
     res = rnd(M, N) if epi == ops.EPI_BIAS_RESIDUAL else None
     ln = (torch.ones(N, device=dev), torch.zeros(N, device=dev), 1e-5) if epi == ops.EPI_BIAS_LN else None
+    kw = {}
+    if lnin:
+        kw["ln_in"] = (torch.rand(K // 64 * M * 2, device=dev) + 0.5, torch.randn(N, device=dev), 1e-5)
+    if stats:
+        kw["stats_out"] = torch.empty(N // 64 * M * 2, device=dev)
     torch.cuda.synchronize()
-    ops.gemm(a, w, bias, epilogue=epi, residual=res, ln=ln)
+    ops.gemm(a, w, bias, epilogue=epi, residual=res, ln=ln, **kw)
     torch.cuda.synchronize()
-    order.append(f"gemm {tag} M{M} N{N} K{K} epi{epi}")
+    order.append(f"gemm {tag} M{M} N{N} K{K} epi{epi} lnin{int(lnin)} stats{int(stats)}")
 
 
 if which in ("gemm", "all"):
     gemm("patch-embed", 903168, 128, 96, ops.EPI_BIAS_LN)
     for st, (M, C) in enumerate([(903168, 128), (225792, 256), (56448, 512), (14112, 1024)], 1):
-        gemm(f"s{st}.qkv", M, 3 * C, C, ops.EPI_BIAS)
-        gemm(f"s{st}.proj", M, C, C, ops.EPI_BIAS_RESIDUAL)
-        gemm(f"s{st}.fc1", M, 4 * C, C, ops.EPI_BIAS_GELU)
-        gemm(f"s{st}.fc2", M, C, 4 * C, ops.EPI_BIAS_RESIDUAL)
+        gemm(f"s{st}.qkv", M, 3 * C, C, ops.EPI_BIAS, lnin=True)
+        gemm(f"s{st}.proj", M, C, C, ops.EPI_BIAS_RESIDUAL, stats=True)
+        gemm(f"s{st}.fc1", M, 4 * C, C, ops.EPI_BIAS_GELU, lnin=True)
+        gemm(f"s{st}.fc2", M, C, 4 * C, ops.EPI_BIAS_RESIDUAL, stats=True)
         if st < 4:
             gemm(f"merge{st}", M // 4, 2 * C, 4 * C, ops.EPI_BIAS)
     gemm("video-proj", 14112, 768, 1024, ops.EPI_BIAS)
     gemm("enc-kv", 14400, 18432, 768, ops.EPI_BIAS)
+
+if which == "pick":  # the few launches worth an `ncu --set full --import-source on` capture
+    gemm("s1.qkv", 903168, 384, 128, ops.EPI_BIAS, lnin=True)
+    gemm("s1.fc1", 903168, 512, 128, ops.EPI_BIAS_GELU, lnin=True)
+    gemm("s3.proj", 56448, 512, 512, ops.EPI_BIAS_RESIDUAL, stats=True)
+    gemm("s3.fc1", 56448, 2048, 512, ops.EPI_BIAS_GELU, lnin=True)
+    qkv = rnd(N_SEG * 588, 1536)
+    bias = ops.window_bias_pack(torch.randn(2535, 16, device=dev) * 0.5)
+    torch.cuda.synchronize()
+    ops.window_attention(qkv, bias, N_SEG, 3, 14, 14, 512, 16, (3, 3))
+    torch.cuda.synchronize()
+    order.append("attn s3 shift(3,3)")
 
 if which in ("attn", "all"):
     for name, hw, C, heads in [("s1", 56, 128, 4), ("s2", 28, 256, 8), ("s3", 14, 512, 16), ("s4", 7, 1024, 32)]:
@@ -62,6 +81,7 @@ if which in ("rows", "all"):
     ops.patch_gather(clips)
     order.append("patch_gather")
     for M, C in [(903168, 128), (225792, 256), (56448, 512), (14112, 1024)]:
+        M = int(M * SC)
         x = rnd(M, C)
         g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
         ops.layernorm(x, g, b, 1e-5)

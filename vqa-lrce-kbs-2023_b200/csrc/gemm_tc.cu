@@ -11,10 +11,12 @@
 //   warp 1      MMA issuer    : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block into TMEM
 //   warp 2      TMEM allocator: 2 accumulator buffers of BN fp32 columns (double-buffered against the epilogue)
 //   warps 4-11  epilogue      : tcgen05.ld (thread = one accumulator row), fused bias / GELU(erf) / residual /
-//                               LayerNorm. Two warps share each 32-lane TMEM quarter and split the columns, so the
-//                               erf-heavy epilogues keep up with the tensor pipe. bf16 tiles leave through two
-//                               128x64 smem slabs (128B-swizzled) and TMA bulk stores, so global writes are full
-//                               lines and the M tail is clipped by the descriptor.
+//                               LayerNorm. Two warps share each 32-lane TMEM quarter and split the 64-column slabs.
+//                               Every warp stages its 32 x 64 bf16 slab in a private 128B-swizzled 4 KB buffer and
+//                               issues its own TMA bulk store (full-line writes, M tail clipped by the descriptor,
+//                               no CTA-wide barrier in the epilogue).
+//   LayerNorm is never a separate pass inside a Swin block: residual epilogues emit per-row (mean, M2) partials of
+//   what they write, and the next GEMM folds the normalisation into its epilogue (see GemmParams::in_stats).
 // Both operands are K-major, so no transposes exist anywhere; M and K tails are handled by TMA zero fill.
 #include "host_common.h"
 #include "lrce_common.cuh"
@@ -33,6 +35,15 @@ struct GemmParams {
   const float* ln_g;  // EPI_BIAS_LN: LayerNorm over the N == BN output features
   const float* ln_b;
   float ln_eps;
+  // LayerNorm folded into the A operand (LNIN kernels): A holds the RAW rows x, W holds W * diag(gamma), and
+  //   out[m, n] = rstd[m] * (acc[m, n] - mean[m] * colsum[n]) + bias'[n]
+  // with (mean, rstd) of row m rebuilt from the per-64-column partials `in_stats` the producing GEMM emitted,
+  // colsum[n] = sum_k W'[n, k] and bias' = bias + W beta (both prepared once at weight-pack time).
+  const float* in_stats;   // float2 [K/64][M]: (mean, M2) of each 64-column chunk of row m (K <= 1024)
+  const float* in_colsum;  // [N]
+  float in_eps;
+  float* out_stats;  // nullptr, or float2 [N/64][M]: (mean, M2) of every 64-column chunk of the output rows (taken before
+                     // the bf16 rounding: the rounding noise shifts the mean by ~2^-9 rms / sqrt(64), far below bf16)
 };
 
 constexpr int GEMM_BM = 128;
@@ -46,31 +57,92 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
-  static constexpr int SLAB_BYTES = GEMM_BM * 64 * 2;  // one 128 x 64 bf16 output slab
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 2 * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SLAB_BYTES = 32 * 64 * 2;  // one epilogue warp's 32-row x 64-column bf16 output slab
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + GEMM_EPI_WARPS * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// bias / GELU / residual on 32 accumulator columns of one row; result packed to 4 x 16 B of bf16
-template <int EPI>
-__device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], int col0, const GemmParams& p, const uint4 (&res)[4],
-                                              uint4 (&o)[4]) {
-  float v[32];
+// erf-GELU (nn.GELU default, video_swin_ori.py:42) as x * sigmoid(2u), u = x (a + b x^2 + c x^4) fitted to the erf form:
+// max |error| 2.6e-5 over all x (well below the bf16 rounding of the result), 7 FMA-pipe ops + 2 MUFU.
+__device__ __forceinline__ float gelu_sig(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  float p = fmaf(0.001014263f, x2, -0.106775716f);
+  p = fmaf(p, x2, -2.3011212f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+
+// (mean, M2) of 32 values
+__device__ __forceinline__ float2 stats32(const float (&v)[32]) {
+  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-  if (p.bias != nullptr) {
+  for (int i = 0; i < 32; ++i) s += v[i];
+  const float mean = s * (1.0f / 32);
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; m2 = fmaf(d, d, m2); }
+  return make_float2(mean, m2);
+}
+// Chan's combination of two equally sized groups of n values each
+__device__ __forceinline__ float2 stats_merge(float2 a, float2 b, float n) {
+  const float d = a.x - b.x;
+  return make_float2(0.5f * (a.x + b.x), a.y + b.y + 0.5f * n * d * d);
+}
+// row statistics of the K-wide LayerNorm input from its K/64 <= 16 chunk partials -> (rstd, -rstd * mean).
+// All partials are fetched with independent loads (one L2 round trip), then combined with Chan's formula.
+__device__ __forceinline__ float2 row_norm_from_stats(const float* stats, int n_chunks, int M, int row, int K, float eps) {
+  const float2* st = reinterpret_cast<const float2*>(stats) + row;
+  float2 t[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) t[c] = (c < n_chunks) ? __ldg(&st[static_cast<size_t>(c) * M]) : make_float2(0.f, 0.f);
+  float sm = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) sm += t[c].x;
+  const float mean = sm / n_chunks;
+  float m2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float d = t[c].x - mean;
+    m2 += (c < n_chunks) ? fmaf(64.0f * d, d, t[c].y) : 0.f;
+  }
+  const float rstd = rsqrtf(m2 / K + eps);
+  return make_float2(rstd, -rstd * mean);
+}
+
+// bias (or folded LayerNorm) / GELU / residual on 32 accumulator columns of one row -> v[32] fp32
+template <int EPI, bool LNIN>
+__device__ __forceinline__ void epilogue_values(const uint32_t (&acc)[32], int col0, const GemmParams& p, float2 rn,
+                                                const uint4 (&res)[4], float (&v)[32]) {
+  if (LNIN) {
+    const float4* c4 = reinterpret_cast<const float4*>(p.in_colsum + col0);
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
-      v[4 * i + 0] += b.x;
-      v[4 * i + 1] += b.y;
-      v[4 * i + 2] += b.z;
-      v[4 * i + 3] += b.w;
+      const float4 c = __ldg(c4 + i), b = __ldg(b4 + i);
+      v[4 * i + 0] = fmaf(rn.x, __uint_as_float(acc[4 * i + 0]), fmaf(rn.y, c.x, b.x));
+      v[4 * i + 1] = fmaf(rn.x, __uint_as_float(acc[4 * i + 1]), fmaf(rn.y, c.y, b.y));
+      v[4 * i + 2] = fmaf(rn.x, __uint_as_float(acc[4 * i + 2]), fmaf(rn.y, c.z, b.z));
+      v[4 * i + 3] = fmaf(rn.x, __uint_as_float(acc[4 * i + 3]), fmaf(rn.y, c.w, b.w));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x;
+        v[4 * i + 1] += b.y;
+        v[4 * i + 2] += b.z;
+        v[4 * i + 3] += b.w;
+      }
     }
   }
   if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_sig(v[i]);
   }
   if (EPI == EPI_BIAS_RESIDUAL) {
 #pragma unroll
@@ -82,6 +154,10 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], int col
       f = unpack_bf16x2(res[i].w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
     }
   }
+}
+
+// round v[32] to bf16, packed into 4 x 16 B
+__device__ __forceinline__ void pack32(const float (&v)[32], uint4 (&o)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     o[i].x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
@@ -91,8 +167,11 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], int col
   }
 }
 
+// fp32 output path (bias epilogue only): direct 16-byte global stores of 32 accumulator columns of one row
 template <int EPI, typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int row, int col0, const GemmParams& p) {
+  static_assert(sizeof(OutT) == 4 && EPI == EPI_BIAS, "direct stores are only used for fp32 output");
+  if (row >= p.M) return;
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
@@ -100,49 +179,19 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int ro
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
+      const float4 b = __ldg(b4 + i);
       v[4 * i + 0] += b.x;
       v[4 * i + 1] += b.y;
       v[4 * i + 2] += b.z;
       v[4 * i + 3] += b.w;
     }
   }
-  if (EPI == EPI_BIAS_GELU) {
+  float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-  }
-  if (row >= p.M) return;
-  if (EPI == EPI_BIAS_RESIDUAL) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ldr + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 r = r4[i];
-      float2 f;
-      f = unpack_bf16x2(r.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-      f = unpack_bf16x2(r.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-      f = unpack_bf16x2(r.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-      f = unpack_bf16x2(r.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
-    }
-  }
-  if (sizeof(OutT) == 2) {
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 o;
-      o.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      o4[i] = o;
-    }
-  } else {
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
+  for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
-template <int BN, int EPI, typename OutT>
+template <int BN, int EPI, typename OutT, bool LNIN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -154,8 +203,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* sC = sB + STAGES * Cfg::B_BYTES;  // 2 output slabs, 1024-byte aligned (stage sizes are multiples of 1024)
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sC + 2 * Cfg::SLAB_BYTES);
+  uint8_t* sC = sB + STAGES * Cfg::B_BYTES;  // 8 per-warp output slabs, 1024-byte aligned (stage sizes are multiples of 1024)
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
@@ -240,11 +289,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;  // which half of the BN columns
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // LN / fp32 paths: which half of the BN columns; TMA path: which 64-column slabs
     constexpr int COLS = BN / 2;
     int it = 0;
-    uint32_t slab_count = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -252,19 +300,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (t % n_tiles_n) * BN;
       const int row_in_tile = q * 32 + lane;
       const int row = m0 + row_in_tile;
-      // residual rows are fetched one 64-column slab ahead (the first one before the accumulator is even ready), so
-      // their latency hides behind the MMA wait / the previous slab's math
-      uint4 res_next[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      const bf16* res_row = nullptr;
-      if (TMA_STORE && EPI == EPI_BIAS_RESIDUAL && row < p.M) {
-        res_row = p.residual + static_cast<size_t>(row) * p.ldr + n0 + half * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row)[i];
-      }
-      mbar_wait(&bar_tfull[as], aphase);
-      tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * COLS;
-      if (EPI == EPI_BIAS_LN) {
+      if constexpr (EPI == EPI_BIAS_LN) {
+        mbar_wait(&bar_tfull[as], aphase);
+        tcgen05_fence_after();
         // full-row LayerNorm: BN == N == 128, this thread holds 64 of the row's 128 features
         float v[COLS];
 #pragma unroll
@@ -275,6 +314,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[c + i] = __uint_as_float(acc[i]) + __ldg(p.bias + half * COLS + c + i);
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[as]);
         float s = 0.f, ss = 0.f;
 #pragma unroll
         for (int i = 0; i < COLS; ++i) { s += v[i]; ss += v[i] * v[i]; }
@@ -289,55 +331,108 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float rstd = rsqrtf(var + p.ln_eps);
         if (row < p.M) {
           bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + half * COLS;
+          float2 st[COLS / 32];
 #pragma unroll
-          for (int i = 0; i < COLS; i += 8) {
-            float y[8];
+          for (int c = 0; c < COLS; c += 32) {
+            float y[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              y[j] = (v[i + j] - mean) * rstd * __ldg(p.ln_g + half * COLS + i + j) + __ldg(p.ln_b + half * COLS + i + j);
-            uint4 o4;
-            o4.x = pack_bf16x2(y[0], y[1]);
-            o4.y = pack_bf16x2(y[2], y[3]);
-            o4.z = pack_bf16x2(y[4], y[5]);
-            o4.w = pack_bf16x2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(o + i) = o4;
+            for (int j = 0; j < 32; ++j)
+              y[j] = (v[c + j] - mean) * rstd * __ldg(p.ln_g + half * COLS + c + j) + __ldg(p.ln_b + half * COLS + c + j);
+            uint4 o4[4];
+            pack32(y, o4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + c + 8 * j) = o4[j];
+            st[c / 32] = stats32(y);
+          }
+          if (p.out_stats != nullptr) {
+            static_assert(BN == 128, "the LayerNorm epilogue emits one 64-column statistics chunk per thread");
+            reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(half) * p.M + row] = stats_merge(st[0], st[1], 32.0f);
           }
         }
-      } else if (TMA_STORE) {
-        // 64-column slabs: the 8 epilogue warps fill one 128 x 64 bf16 slab (this warp: 32 rows x 32 columns), then one
-        // thread hands it to the TMA store engine; two slabs alternate so the store of slab g overlaps the math of g+1.
-        const bool leader = (warp == 4 && lane == 0);
-#pragma unroll 1
-        for (int sl = 0; sl < BN / 64; ++sl, ++slab_count) {
-          uint32_t acc[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + sl * 64 + half * 32, acc);
+      } else if constexpr (TMA_STORE) {
+        // Each warp owns the 64-column slabs sl = half, half + 2, ... of its 32 rows: tcgen05.ld -> math -> private
+        // swizzled 4 KB staging slab -> its own TMA bulk store. No CTA-wide barrier: a warp only ever waits for its own
+        // previous store to have drained the slab, and the accumulator is released right after its last tcgen05.ld.
+        constexpr int MY_SLABS = BN / 128;
+        uint8_t* slab = sC + (warp - 4) * Cfg::SLAB_BYTES;
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+        float2 rn = make_float2(1.f, 0.f);
+        if (LNIN && row < p.M) rn = row_norm_from_stats(p.in_stats, p.K / 64, p.M, row, p.K, p.in_eps);
+        // residual rows are fetched one 32-column piece ahead (the first one before the accumulator is even ready)
+        uint4 res_next[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        const bf16* res_row = nullptr;
+        if (EPI == EPI_BIAS_RESIDUAL && row < p.M) {
+          res_row = p.residual + static_cast<size_t>(row) * p.ldr + n0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row + half * 64)[i];
+        }
+        mbar_wait(&bar_tfull[as], aphase);
+        tcgen05_fence_after();
+        uint32_t acc[2][32];
+        float2 st_carry = make_float2(0.f, 0.f);
+        tmem_ld_32x32(tq + half * 64, acc[0]);
+#pragma unroll
+        for (int pc = 0; pc < 2 * MY_SLABS; ++pc) {  // 32-column pieces; two per slab
+          const int sl = half + 2 * (pc >> 1);
+          const int col_in_tile = sl * 64 + (pc & 1) * 32;
+          tmem_ld_wait();
+          if (pc + 1 < 2 * MY_SLABS) {
+            const int nsl = half + 2 * ((pc + 1) >> 1);
+            tmem_ld_32x32(tq + nsl * 64 + ((pc + 1) & 1) * 32, acc[(pc + 1) & 1]);
+          }
           uint4 res_cur[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
-          if (EPI == EPI_BIAS_RESIDUAL && res_row != nullptr && sl + 1 < BN / 64) {
+          if (EPI == EPI_BIAS_RESIDUAL && res_row != nullptr && pc + 1 < 2 * MY_SLABS) {
+            const int nsl = half + 2 * ((pc + 1) >> 1);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row + (sl + 1) * 64)[i];
+            for (int i = 0; i < 4; ++i)
+              res_next[i] = reinterpret_cast<const uint4*>(res_row + nsl * 64 + ((pc + 1) & 1) * 32)[i];
           }
-          tmem_ld_wait();
+          float v[32];
+          epilogue_values<EPI, LNIN>(acc[pc & 1], n0 + col_in_tile, p, rn, res_cur, v);
           uint4 o[4];
-          epilogue_math<EPI>(acc, n0 + sl * 64 + half * 32, p, res_cur, o);
-          uint8_t* slab = sC + (slab_count & 1) * Cfg::SLAB_BYTES + row_in_tile * 128;
+          pack32(v, o);
+          float2 st_piece = make_float2(0.f, 0.f);
+          if (p.out_stats != nullptr) st_piece = stats32(v);
+          if ((pc & 1) == 0) {
+            // the previous TMA store of this warp must have finished reading the slab before it is refilled
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)  // 128B swizzle: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
-            *reinterpret_cast<uint4*>(slab + (((half * 4 + i) ^ (row_in_tile & 7)) << 4)) = o[i];
-          fence_proxy_async_smem();
-          // the store issued one slab ago must have drained its smem reads before anyone re-fills that buffer next turn
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (leader) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmC)),
-                         "r"(smem_u32(sC + (slab_count & 1) * Cfg::SLAB_BYTES)), "r"(n0 + sl * 64), "r"(m0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            *reinterpret_cast<uint4*>(slab + lane * 128 + ((((pc & 1) * 4 + i) ^ (lane & 7)) << 4)) = o[i];
+          static_assert(MY_SLABS <= 2, "stats carry below assumes at most two slabs per warp");
+          if (pc & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(smem_u32(slab)), "r"(n0 + sl * 64), "r"(m0 + q * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (p.out_stats != nullptr) {
+            if ((pc & 1) == 0) {
+              st_carry = st_piece;
+            } else if (row < p.M) {
+              reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>((n0 >> 6) + sl) * p.M + row] =
+                  stats_merge(st_carry, st_piece, 32.0f);
+            }
+          }
+          if (pc + 1 == 2 * MY_SLABS) {
+            // every tcgen05.ld of this tile has completed (wait::ld at the top of this iteration): release the accumulator
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[as]);
           }
         }
-      } else {
+      } else if constexpr (sizeof(OutT) == 4) {
+        mbar_wait(&bar_tfull[as], aphase);
+        tcgen05_fence_after();
 #pragma unroll 1
         for (int c = 0; c < COLS; c += 32) {
           uint32_t acc[32];
@@ -345,12 +440,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           epilogue_chunk<EPI, OutT>(acc, row, n0 + half * COLS + c, p);
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[as]);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[as]);
     }
-    if (TMA_STORE && warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
@@ -361,11 +456,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, int EPI, typename OutT>
+template <int BN, int EPI, typename OutT, bool LNIN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, EPI, OutT>;
+  auto kern = gemm_tc_kernel<BN, EPI, OutT, LNIN>;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -385,14 +480,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 template <int BN>
 static int dispatch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int epi,
                         int out_fp32, cudaStream_t stream) {
+  const bool lnin = p.in_stats != nullptr;
   if (out_fp32) {
-    LRCE_REQUIRE(epi == EPI_BIAS, "fp32 output is only available with the bias epilogue (epi=%d)", epi);
-    return launch_gemm<BN, EPI_BIAS, float>(tmA, tmB, tmC, p, stream);
+    LRCE_REQUIRE(epi == EPI_BIAS && !lnin, "fp32 output is only available with the plain bias epilogue (epi=%d)", epi);
+    return launch_gemm<BN, EPI_BIAS, float, false>(tmA, tmB, tmC, p, stream);
   }
   switch (epi) {
-    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS, bf16>(tmA, tmB, tmC, p, stream);
-    case EPI_BIAS_GELU: return launch_gemm<BN, EPI_BIAS_GELU, bf16>(tmA, tmB, tmC, p, stream);
-    case EPI_BIAS_RESIDUAL: return launch_gemm<BN, EPI_BIAS_RESIDUAL, bf16>(tmA, tmB, tmC, p, stream);
+    case EPI_BIAS:
+      return lnin ? launch_gemm<BN, EPI_BIAS, bf16, true>(tmA, tmB, tmC, p, stream)
+                  : launch_gemm<BN, EPI_BIAS, bf16, false>(tmA, tmB, tmC, p, stream);
+    case EPI_BIAS_GELU:
+      return lnin ? launch_gemm<BN, EPI_BIAS_GELU, bf16, true>(tmA, tmB, tmC, p, stream)
+                  : launch_gemm<BN, EPI_BIAS_GELU, bf16, false>(tmA, tmB, tmC, p, stream);
+    case EPI_BIAS_RESIDUAL:
+      LRCE_REQUIRE(!lnin, "the residual epilogue does not take a folded LayerNorm input");
+      return launch_gemm<BN, EPI_BIAS_RESIDUAL, bf16, false>(tmA, tmB, tmC, p, stream);
     default: break;
   }
   set_error("unknown GEMM epilogue %d", epi);
@@ -405,7 +507,8 @@ using namespace lrce;
 
 extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                               const void* residual, int ldr, void* out, int ldo, int epilogue, int out_fp32,
-                              const float* ln_gamma, const float* ln_beta, float ln_eps, void* stream) {
+                              const float* ln_gamma, const float* ln_beta, float ln_eps, const float* in_stats,
+                              const float* in_colsum, float in_eps, float* out_stats, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(A && W && out, "lrce_gemm_bf16: null operand");
@@ -417,6 +520,13 @@ extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   if (epilogue == EPI_BIAS_RESIDUAL)
     LRCE_REQUIRE(residual && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                  "lrce_gemm_bf16: residual epilogue needs a 16B-aligned residual");
+  if (in_stats != nullptr)
+    LRCE_REQUIRE(in_colsum && bias && K % 64 == 0 && K <= 1024 && (reinterpret_cast<uintptr_t>(in_colsum) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(in_stats) & 7) == 0,
+                 "lrce_gemm_bf16: a folded LayerNorm input needs statistics, column sums, a bias and K %% 64 == 0 (K=%d)", K);
+  if (out_stats != nullptr)
+    LRCE_REQUIRE(!out_fp32 && (reinterpret_cast<uintptr_t>(out_stats) & 7) == 0,
+                 "lrce_gemm_bf16: row statistics are emitted for bf16 outputs only");
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.bias = bias;
@@ -425,22 +535,24 @@ extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   p.out = out;
   p.ldo = ldo;
   p.ln_g = ln_gamma; p.ln_b = ln_beta; p.ln_eps = ln_eps;
+  p.in_stats = in_stats; p.in_colsum = in_colsum; p.in_eps = in_eps;
+  p.out_stats = out_stats;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB, tmC;
   rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, GEMM_BK, GEMM_BM);
   if (rc != LRCE_OK) return rc;
-  if (!out_fp32 && epilogue != EPI_BIAS_LN) {  // bf16 tiles are written by TMA stores of 128 x 64 slabs
-    rc = make_tmap_2d_bf16(&tmC, out, N, M, ldo, 64, GEMM_BM);
+  if (!out_fp32 && epilogue != EPI_BIAS_LN) {  // bf16 tiles leave as per-warp TMA stores of 32-row x 64-column slabs
+    rc = make_tmap_2d_bf16(&tmC, out, N, M, ldo, 64, 32);
     if (rc != LRCE_OK) return rc;
   } else {
     tmC = tmA;  // unused by these epilogues
   }
   if (epilogue == EPI_BIAS_LN) {
-    LRCE_REQUIRE(N == 128 && bias && ln_gamma && ln_beta && !out_fp32,
+    LRCE_REQUIRE(N == 128 && bias && ln_gamma && ln_beta && !out_fp32 && !in_stats,
                  "lrce_gemm_bf16: the LayerNorm epilogue needs N == 128, a bias and gamma/beta (N=%d)", N);
     rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, GEMM_BK, 128);
     if (rc != LRCE_OK) return rc;
-    return launch_gemm<128, EPI_BIAS_LN, bf16>(tmA, tmB, tmC, p, s);
+    return launch_gemm<128, EPI_BIAS_LN, bf16, false>(tmA, tmB, tmC, p, s);
   }
   const bool wide = (N % 256 == 0);
   rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, GEMM_BK, wide ? 256 : 128);

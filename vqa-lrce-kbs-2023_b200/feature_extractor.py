@@ -152,11 +152,20 @@ class SwinTransformer3D(nn.Module):
         for layer in self.layers:
             blocks = []
             for blk in layer.blocks:
+                # norm1 / norm2 are folded into the qkv / fc1 GEMMs (lrce_gemm_bf16 `in_stats`): W' = W diag(gamma) in
+                # bf16, colsum = row sums of the ROUNDED W' (what the tensor core multiplies), bias' = bias + W beta
+                def fold(lin, norm):
+                    w = lin.weight.detach().to(dev, torch.float64)
+                    wg = (w * norm.weight.detach().to(dev, torch.float64)[None, :]).to(torch.bfloat16).contiguous()
+                    colsum = wg.to(torch.float64).sum(1).float().contiguous()
+                    bias = (lin.bias.detach().to(dev, torch.float64) + w @ norm.bias.detach().to(dev, torch.float64))
+                    return wg, colsum, bias.float().contiguous()
+
+                wqkv, cqkv, bqkv = fold(blk.attn.qkv, blk.norm1)
+                w1, c1, b1 = fold(blk.mlp.fc1, blk.norm2)
                 blocks.append(dict(
-                    n1g=f32(blk.norm1.weight), n1b=f32(blk.norm1.bias), n2g=f32(blk.norm2.weight), n2b=f32(blk.norm2.bias),
-                    wqkv=bf(blk.attn.qkv.weight), bqkv=f32(blk.attn.qkv.bias), wproj=bf(blk.attn.proj.weight),
-                    bproj=f32(blk.attn.proj.bias), w1=bf(blk.mlp.fc1.weight), b1=f32(blk.mlp.fc1.bias),
-                    w2=bf(blk.mlp.fc2.weight), b2=f32(blk.mlp.fc2.bias),
+                    wqkv=wqkv, cqkv=cqkv, bqkv=bqkv, wproj=bf(blk.attn.proj.weight), bproj=f32(blk.attn.proj.bias),
+                    w1=w1, c1=c1, b1=b1, w2=bf(blk.mlp.fc2.weight), b2=f32(blk.mlp.fc2.bias),
                     bias=ops.window_bias_pack(f32(blk.attn.relative_position_bias_table))))
             ds = None
             if layer.downsample is not None:
@@ -176,7 +185,12 @@ class SwinTransformer3D(nn.Module):
         if D != 3 or H % 7 or W % 7:
             raise ops._lib.LrceError("the window-attention kernel needs 5/6-frame segments and H, W multiples of 28")
         a = ops.patch_gather(clips)
-        x = ops.gemm(a, pk["pe_w"], pk["pe_b"], epilogue=ops.EPI_BIAS_LN, ln=(pk["pe_g"], pk["pe_beta"], 1e-5))
+        M = a.shape[0]
+        # per-row LayerNorm partials (mean, M2 per 64-column chunk) travel from each GEMM that writes the residual
+        # stream to the next GEMM that reads it through a LayerNorm; two buffers alternate (norm1 / norm2)
+        st_a = torch.empty(M * self.embed_dim // 32, device=a.device, dtype=torch.float32)  # [C/64, M, 2] at any stage
+        st_b = torch.empty_like(st_a)
+        x = ops.gemm(a, pk["pe_w"], pk["pe_b"], epilogue=ops.EPI_BIAS_LN, ln=(pk["pe_g"], pk["pe_beta"], 1e-5), stats_out=st_a)
         if taps is not None:
             taps["patch_embed"] = x.view(n, D, H, W, -1).clone()
         C = self.embed_dim
@@ -184,20 +198,19 @@ class SwinTransformer3D(nn.Module):
             heads = self.num_heads[i]
             shift = (3, 3) if H > 7 else (0, 0)  # clamped axes are never shifted (video_swin_ori.py:91-104)
             for j, b in enumerate(st["blocks"]):
-                xn = ops.layernorm(x, b["n1g"], b["n1b"], 1e-5)
-                qkv = ops.gemm(xn, b["wqkv"], b["bqkv"])
-                att = ops.window_attention(qkv, b["bias"], n, D, H, W, C, heads, shift if j % 2 else (0, 0), out=xn)
+                qkv = ops.gemm(x, b["wqkv"], b["bqkv"], ln_in=(st_a, b["cqkv"], 1e-5))
+                att = ops.window_attention(qkv, b["bias"], n, D, H, W, C, heads, shift if j % 2 else (0, 0))
                 del qkv
-                ops.gemm(att, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x)
-                xn = ops.layernorm(x, b["n2g"], b["n2b"], 1e-5, out=att)
-                hid = ops.gemm(xn, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU)
-                ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x)
+                ops.gemm(att, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_b)
+                del att
+                hid = ops.gemm(x, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU, ln_in=(st_b, b["c1"], 1e-5))
+                ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_a)
                 del hid
                 if taps is not None and j < 2 and i < 3:
                     taps[f"stage{i}.block{j}"] = x.view(n, D, H, W, C).clone()
             if st["ds"] is not None:
                 y = ops.patch_merge_ln(x, st["ds"]["g"], st["ds"]["b"], 1e-5, n, D, H, W, C)
-                x = ops.gemm(y, st["ds"]["w"], None)
+                x = ops.gemm(y, st["ds"]["w"], None, stats_out=st_a)
                 H, W, C = H // 2, W // 2, 2 * C
             if taps is not None:
                 taps[f"stage{i}.out"] = x.view(n, D, H, W, C).clone()

@@ -46,16 +46,17 @@ const char* lrce_last_error(void);
  * nn.TransformerDecoderLayer built at fusionv3.py:8-17.
  *
  * LayerNorm folding (norm1 -> qkv, norm2 -> fc1; video_swin_ori.py:252,:285): instead of a separate LayerNorm pass,
- *  - a producing GEMM called with out_stats != NULL also writes float2 out_stats[N/64][M] = (mean, M2) of every
- *    64-column chunk of the rows it stores (taken just before the bf16 rounding);
- *  - a consuming GEMM called with in_stats != NULL (float2 [K/64][M]) takes A = the RAW rows, W = W * diag(gamma),
+ *  - a producing GEMM called with out_stats != NULL also writes float2 out_stats[N/cw][M] = (mean, M2) of every
+ *    cw-column chunk of the rows it stores (taken just before the bf16 rounding); cw = 64 when N % 256 == 0, else 32;
+ *  - a consuming GEMM called with in_stats != NULL (float2 [K/in_chunk][M], in_chunk = the producer's cw, at most 16
+ *    chunks) takes A = the RAW rows, W = W * diag(gamma),
  *    in_colsum[n] = sum_k W'[n,k], bias = bias + W beta, and computes
  *    out[m,n] = epilogue(rstd[m] * (acc[m,n] - mean[m] * in_colsum[n]) + bias[n]) with (mean, rstd) of row m rebuilt
  *    from the partials (Chan's combination, eps = in_eps). Exactly LayerNorm(x) W^T + b in exact arithmetic.
- * in_stats requires K % 64 == 0 and the BIAS or BIAS_GELU epilogue; out_stats requires bf16 output. */
+ * in_stats requires the BIAS or BIAS_GELU epilogue; out_stats requires bf16 output. */
 int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                    const void* residual, int ldr, void* out, int ldo, int epilogue, int out_fp32,
-                   const float* ln_gamma, const float* ln_beta, float ln_eps, const float* in_stats,
+                   const float* ln_gamma, const float* ln_beta, float ln_eps, const float* in_stats, int in_chunk,
                    const float* in_colsum, float in_eps, float* out_stats, void* stream);
 
 /* ---- HBM-bound row kernels (Video Swin) --------------------------------------------------------------------- */

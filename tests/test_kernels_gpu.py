@@ -73,9 +73,11 @@ def test_window_remap_tensor_bit_exact(ops, name, C):
 
 
 def chunk_stats(x):
-    """torch statement of the LayerNorm partials a producing GEMM emits: (M, C) bf16 -> fp32 [C/64, M, 2] = (mean, M2)"""
+    """torch statement of the LayerNorm partials a producing GEMM emits: (M, C) bf16 -> fp32 [C/cw, M, 2] = (mean, M2),
+    cw = 64 columns when C % 256 == 0, else 32 (ops.stats_chunk)"""
     M, C = x.shape
-    v = x.float().view(M, C // 64, 64)
+    cw = 64 if C % 256 == 0 else 32
+    v = x.float().view(M, C // cw, cw)
     mean = v.mean(-1)
     m2 = ((v - mean[..., None]) ** 2).sum(-1)
     return torch.stack([mean, m2], -1).permute(1, 0, 2).contiguous()
@@ -106,7 +108,7 @@ def test_gemm_layernorm_folded_input(ops, M, N, K, epi):
                                        (700, 128, 96, "ln")])
 def test_gemm_emits_row_statistics(ops, M, N, K, epi):
     a, w, b = seeded((M, K), 6, 0.5).bfloat16().cuda(), seeded((N, K), 7, 0.05).bfloat16().cuda(), seeded((N,), 8).cuda()
-    st = torch.zeros(N // 64 * M * 2, device="cuda")
+    st = torch.zeros(N // ops.stats_chunk(N) * M * 2, device="cuda")
     if epi == "res":
         r = seeded((M, N), 9).bfloat16().cuda()
         y = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_RESIDUAL, residual=r, stats_out=st)
@@ -120,7 +122,7 @@ def test_gemm_emits_row_statistics(ops, M, N, K, epi):
         ref = a.float() @ w.float().t() + b
     assert rel_l2(y, ref) < 6e-3
     want = chunk_stats(y)  # the kernel takes them just before the bf16 rounding of y: equal up to the rounding noise
-    got = st.view(N // 64, M, 2)
+    got = st.view(N // ops.stats_chunk(N), M, 2)
     assert (got[..., 0] - want[..., 0]).abs().max().item() < 2e-3 * max(1.0, y.float().abs().max().item())
     assert ((got[..., 1] - want[..., 1]).abs() / want[..., 1].clamp_min(1e-3)).max().item() < 2e-2
 
@@ -233,7 +235,7 @@ def test_swin_block_vs_reference_golden(ops, golden, swin_cuda, tag, layer, blk,
     x0 = seeded((1, 3, hw, hw, dim), 100 + layer * 10 + blk)
     x = x0.bfloat16().cuda().view(-1, dim).clone()
     shift = (3, 3) if (blk % 2 and hw > 7) else (0, 0)
-    st_a, st_b = chunk_stats(x), torch.empty(dim // 64 * x.shape[0] * 2, device="cuda")
+    st_a, st_b = chunk_stats(x), torch.empty(dim // 32 * x.shape[0] * 2, device="cuda")
     qkv = ops.gemm(x, pk["wqkv"], pk["bqkv"], ln_in=(st_a, pk["cqkv"], 1e-5))
     att = ops.window_attention(qkv, pk["bias"], 1, 3, hw, hw, dim, heads, shift)
     ops.gemm(att, pk["wproj"], pk["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_b)

@@ -46,9 +46,9 @@ def bench(M, N, K, epi, iters=20, lnin=False, stats=False):
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     kw = {}
     if lnin:
-        kw["ln_in"] = (torch.rand(K // 64 * M * 2, device=dev) + 0.5, torch.randn(N, device=dev), 1e-5)
+        kw["ln_in"] = (torch.rand(K // 32 * M * 2, device=dev) + 0.5, torch.randn(N, device=dev), 1e-5)
     if stats:
-        kw["stats_out"] = torch.empty(N // 64 * M * 2, device=dev)
+        kw["stats_out"] = torch.empty(N // 32 * M * 2, device=dev)
     for _ in range(3):
         ops.gemm(a, w, bias, epilogue=epi, residual=res, out=out, **kw)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -32,9 +32,9 @@ def gemm(tag, M, N, K, epi, lnin=False, stats=False):
     ln = (torch.ones(N, device=dev), torch.zeros(N, device=dev), 1e-5) if epi == ops.EPI_BIAS_LN else None
     kw = {}
     if lnin:
-        kw["ln_in"] = (torch.rand(K // 64 * M * 2, device=dev) + 0.5, torch.randn(N, device=dev), 1e-5)
+        kw["ln_in"] = (torch.rand(K // 32 * M * 2, device=dev) + 0.5, torch.randn(N, device=dev), 1e-5)
     if stats:
-        kw["stats_out"] = torch.empty(N // 64 * M * 2, device=dev)
+        kw["stats_out"] = torch.empty(N // 32 * M * 2, device=dev)
     torch.cuda.synchronize()
     ops.gemm(a, w, bias, epilogue=epi, residual=res, ln=ln, **kw)
     torch.cuda.synchronize()

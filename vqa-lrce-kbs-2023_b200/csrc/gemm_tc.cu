@@ -39,17 +39,19 @@ struct GemmParams {
   //   out[m, n] = rstd[m] * (acc[m, n] - mean[m] * colsum[n]) + bias'[n]
   // with (mean, rstd) of row m rebuilt from the per-64-column partials `in_stats` the producing GEMM emitted,
   // colsum[n] = sum_k W'[n, k] and bias' = bias + W beta (both prepared once at weight-pack time).
-  const float* in_stats;   // float2 [K/64][M]: (mean, M2) of each 64-column chunk of row m (K <= 1024)
+  const float* in_stats;   // float2 [K/in_chunk][M]: (mean, M2) of each in_chunk-column chunk of row m (<= 16 chunks)
+  int in_chunk;            // 32 or 64
   const float* in_colsum;  // [N]
   float in_eps;
-  float* out_stats;  // nullptr, or float2 [N/64][M]: (mean, M2) of every 64-column chunk of the output rows (taken before
-                     // the bf16 rounding: the rounding noise shifts the mean by ~2^-9 rms / sqrt(64), far below bf16)
+  float* out_stats;  // nullptr, or float2 [N/cw][M]: (mean, M2) of every cw-column chunk of the output rows, cw = 32 for
+                     // the 128-wide tile kernels (N % 256 != 0) and 64 otherwise (taken before the bf16 rounding: the
+                     // rounding noise shifts the mean by ~2^-9 rms / sqrt(cw), far below bf16)
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 640;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, row-statistics; warps 4-19: epilogue
+constexpr int GEMM_EPI_WARPS = 16;  // four per TMEM lane quarter, each owning a quarter of the tile's columns
 
 template <int BN>
 struct GemmCfg {
@@ -57,8 +59,9 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
-  static constexpr int SLAB_BYTES = 32 * 64 * 2;  // one epilogue warp's 32-row x 64-column bf16 output slab
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + GEMM_EPI_WARPS * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SLAB_BYTES = 32 * 32 * 2;  // one epilogue warp's 32-row x 32-column bf16 output slab (64B-swizzled)
+  static constexpr int RN_BYTES = 2 * GEMM_BM * 8;  // (rstd, -rstd*mean) of the rows of two tiles in flight
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + GEMM_EPI_WARPS * SLAB_BYTES + RN_BYTES + 256 /*barriers*/;
 };
 
 // erf-GELU (nn.GELU default, video_swin_ori.py:42) as x * sigmoid(2u), u = x (a + b x^2 + c x^4) fitted to the erf form:
@@ -89,25 +92,37 @@ __device__ __forceinline__ float2 stats_merge(float2 a, float2 b, float n) {
   const float d = a.x - b.x;
   return make_float2(0.5f * (a.x + b.x), a.y + b.y + 0.5f * n * d * d);
 }
-// row statistics of the K-wide LayerNorm input from its K/64 <= 16 chunk partials -> (rstd, -rstd * mean).
-// All partials are fetched with independent loads (one L2 round trip), then combined with Chan's formula.
-__device__ __forceinline__ float2 row_norm_from_stats(const float* stats, int n_chunks, int M, int row, int K, float eps) {
-  const float2* st = reinterpret_cast<const float2*>(stats) + row;
-  float2 t[16];
+// Row statistics of the K-wide LayerNorm input from its NC = K/cw chunk partials -> (rstd, -rstd * mean), for the
+// ROWS rows lane + 32 * (i0 + i) of one 128-row tile. `stats_fetch` issues every load (they are independent: one L2
+// round trip for the whole batch), `stats_reduce` combines the partials with Chan's formula.
+template <int NC, int ROWS>
+__device__ __forceinline__ void stats_fetch(float2 (&t)[ROWS][NC], const float* stats, int M, int m0, int lane, int i0) {
 #pragma unroll
-  for (int c = 0; c < 16; ++c) t[c] = (c < n_chunks) ? __ldg(&st[static_cast<size_t>(c) * M]) : make_float2(0.f, 0.f);
-  float sm = 0.f;
+  for (int i = 0; i < ROWS; ++i) {
+    const int row = min(m0 + lane + 32 * (i0 + i), M - 1);  // tail rows of the last tile read a valid row, never stored
+    const float2* st = reinterpret_cast<const float2*>(stats) + row;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) sm += t[c].x;
-  const float mean = sm / n_chunks;
-  float m2 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const float d = t[c].x - mean;
-    m2 += (c < n_chunks) ? fmaf(64.0f * d, d, t[c].y) : 0.f;
+    for (int c = 0; c < NC; ++c) t[i][c] = __ldg(&st[static_cast<size_t>(c) * M]);
   }
-  const float rstd = rsqrtf(m2 / K + eps);
-  return make_float2(rstd, -rstd * mean);
+}
+template <int NC, int ROWS>
+__device__ __forceinline__ void stats_reduce(const float2 (&t)[ROWS][NC], float2* s_rn, int lane, int i0, float cw, int K,
+                                             float eps) {
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    float sm = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sm += t[i][c].x;
+    const float mean = sm * (1.0f / NC);
+    float m2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float d = t[i][c].x - mean;
+      m2 += fmaf(cw * d, d, t[i][c].y);
+    }
+    const float rstd = rsqrtf(m2 / K + eps);
+    s_rn[lane + 32 * (i0 + i)] = make_float2(rstd, -rstd * mean);
+  }
 }
 
 // bias (or folded LayerNorm) / GELU / residual on 32 accumulator columns of one row -> v[32] fp32
@@ -198,18 +213,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool TMA_STORE = (sizeof(OutT) == 2) && (EPI != EPI_BIAS_LN);
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int WCOLS = BN / 4;      // columns of the tile owned by one epilogue warp
+  constexpr int PIECES = WCOLS / 32;  // 32-column pieces per warp and tile
   // 1024-byte alignment is required by the 128B swizzle atoms; the pointer stays derived from the __shared__ array so
   // that the epilogue's slab writes compile to STS (an integer round trip would demote them to generic stores)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* sC = sB + STAGES * Cfg::B_BYTES;  // 8 per-warp output slabs, 1024-byte aligned (stage sizes are multiples of 1024)
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES);
+  uint8_t* sC = sB + STAGES * Cfg::B_BYTES;  // 16 per-warp output slabs (stage sizes are multiples of 1024)
+  float2* s_rn = reinterpret_cast<float2*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES + Cfg::RN_BYTES);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
-  // LayerNorm epilogue scratch [tile parity][column half][sum | sumsq][row] aliases the (then unused) output slabs
+  uint64_t* bar_rnfull = bar_tempty + 2;
+  uint64_t* bar_rnempty = bar_rnfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_rnempty + 2);
+  // LayerNorm epilogue scratch [tile parity][column quarter][sum | sumsq][row] aliases the (then unused) output slabs
   float* ln_part = reinterpret_cast<float*>(sC);
 
   const int warp = threadIdx.x >> 5;
@@ -232,6 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bar_tfull[a], 1);
       mbar_init(&bar_tempty[a], GEMM_EPI_WARPS);
+      mbar_init(&bar_rnfull[a], 1);
+      mbar_init(&bar_rnempty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -287,11 +309,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&bar_tfull[as]);
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ row statistics of the folded LayerNorm
+    // runs one tile ahead of the epilogue: the L2 round trip for the partials never sits on the epilogue's path
+    if (LNIN) {
+      const int n_chunks = p.K / p.in_chunk;
+      const float cw = static_cast<float>(p.in_chunk);
+      auto publish = [&](int it) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_rnfull[it & 1]);
+      };
+      if (n_chunks == 4) {
+        // narrow rows (C = 128 / 256): tiles are short, so the partials of tile i+1 are already in flight while tile i
+        // is reduced (two register sets, loop unrolled by two)
+        float2 ta[4][4], tb[4][4];
+        int t = blockIdx.x, it = 0;
+        if (t < n_tiles) stats_fetch<4, 4>(ta, p.in_stats, p.M, (t / n_tiles_n) * GEMM_BM, lane, 0);
+        while (t < n_tiles) {
+          int tn = t + gridDim.x;
+          if (tn < n_tiles) stats_fetch<4, 4>(tb, p.in_stats, p.M, (tn / n_tiles_n) * GEMM_BM, lane, 0);
+          mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+          stats_reduce<4, 4>(ta, s_rn + (it & 1) * GEMM_BM, lane, 0, cw, p.K, p.in_eps);
+          publish(it);
+          t = tn; ++it;
+          if (t >= n_tiles) break;
+          tn = t + gridDim.x;
+          if (tn < n_tiles) stats_fetch<4, 4>(ta, p.in_stats, p.M, (tn / n_tiles_n) * GEMM_BM, lane, 0);
+          mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+          stats_reduce<4, 4>(tb, s_rn + (it & 1) * GEMM_BM, lane, 0, cw, p.K, p.in_eps);
+          publish(it);
+          t = tn; ++it;
+        }
+      } else {
+        int it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+          const int m0 = (t / n_tiles_n) * GEMM_BM;
+          float2* dst = s_rn + (it & 1) * GEMM_BM;
+          if (n_chunks == 8) {
+            float2 ta[4][8];
+            stats_fetch<8, 4>(ta, p.in_stats, p.M, m0, lane, 0);
+            mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+            stats_reduce<8, 4>(ta, dst, lane, 0, cw, p.K, p.in_eps);
+          } else {  // 16 chunks (host-checked): two rows at a time
+            mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+#pragma unroll 1
+            for (int i0 = 0; i0 < 4; i0 += 2) {
+              float2 ta[2][16];
+              stats_fetch<16, 2>(ta, p.in_stats, p.M, m0, lane, i0);
+              stats_reduce<16, 2>(ta, dst, lane, i0, cw, p.K, p.in_eps);
+            }
+          }
+          publish(it);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;  // LN / fp32 paths: which half of the BN columns; TMA path: which 64-column slabs
-    constexpr int COLS = BN / 2;
+    const int part = (warp - 4) >> 2;  // which quarter of the tile's columns
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -300,145 +375,134 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (t % n_tiles_n) * BN;
       const int row_in_tile = q * 32 + lane;
       const int row = m0 + row_in_tile;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * COLS;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + part * WCOLS;
       if constexpr (EPI == EPI_BIAS_LN) {
+        static_assert(BN == 128 || EPI != EPI_BIAS_LN, "the LayerNorm epilogue normalises over one 128-wide tile");
         mbar_wait(&bar_tfull[as], aphase);
         tcgen05_fence_after();
-        // full-row LayerNorm: BN == N == 128, this thread holds 64 of the row's 128 features
-        float v[COLS];
-#pragma unroll
-        for (int c = 0; c < COLS; c += 32) {
+        // full-row LayerNorm: BN == N == 128, this thread holds 32 of the row's 128 features
+        float v[32];
+        {
           uint32_t acc[32];
-          tmem_ld_32x32(taddr + c, acc);
+          tmem_ld_32x32(taddr, acc);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[c + i] = __uint_as_float(acc[i]) + __ldg(p.bias + half * COLS + c + i);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + __ldg(p.bias + part * 32 + i);
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[as]);
         float s = 0.f, ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < COLS; ++i) { s += v[i]; ss += v[i] * v[i]; }
+        for (int i = 0; i < 32; ++i) { s += v[i]; ss += v[i] * v[i]; }
         const int par = it & 1;
-        ln_part[((par * 2 + half) * 2 + 0) * GEMM_BM + row_in_tile] = s;
-        ln_part[((par * 2 + half) * 2 + 1) * GEMM_BM + row_in_tile] = ss;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        s += ln_part[((par * 2 + (half ^ 1)) * 2 + 0) * GEMM_BM + row_in_tile];
-        ss += ln_part[((par * 2 + (half ^ 1)) * 2 + 1) * GEMM_BM + row_in_tile];
+        ln_part[((par * 4 + part) * 2 + 0) * GEMM_BM + row_in_tile] = s;
+        ln_part[((par * 4 + part) * 2 + 1) * GEMM_BM + row_in_tile] = ss;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        s = ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          s += ln_part[((par * 4 + k) * 2 + 0) * GEMM_BM + row_in_tile];
+          ss += ln_part[((par * 4 + k) * 2 + 1) * GEMM_BM + row_in_tile];
+        }
         const float mean = s * (1.0f / BN);
         const float var = fmaxf(ss * (1.0f / BN) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.ln_eps);
         if (row < p.M) {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + half * COLS;
-          float2 st[COLS / 32];
+          bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + part * 32;
+          float y[32];
 #pragma unroll
-          for (int c = 0; c < COLS; c += 32) {
-            float y[32];
+          for (int j = 0; j < 32; ++j)
+            y[j] = (v[j] - mean) * rstd * __ldg(p.ln_g + part * 32 + j) + __ldg(p.ln_b + part * 32 + j);
+          uint4 o4[4];
+          pack32(y, o4);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              y[j] = (v[c + j] - mean) * rstd * __ldg(p.ln_g + half * COLS + c + j) + __ldg(p.ln_b + half * COLS + c + j);
-            uint4 o4[4];
-            pack32(y, o4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + c + 8 * j) = o4[j];
-            st[c / 32] = stats32(y);
-          }
-          if (p.out_stats != nullptr) {
-            static_assert(BN == 128, "the LayerNorm epilogue emits one 64-column statistics chunk per thread");
-            reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(half) * p.M + row] = stats_merge(st[0], st[1], 32.0f);
-          }
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = o4[j];
+          if (p.out_stats != nullptr)
+            reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(part) * p.M + row] = stats32(y);
         }
       } else if constexpr (TMA_STORE) {
-        // Each warp owns the 64-column slabs sl = half, half + 2, ... of its 32 rows: tcgen05.ld -> math -> private
-        // swizzled 4 KB staging slab -> its own TMA bulk store. No CTA-wide barrier: a warp only ever waits for its own
-        // previous store to have drained the slab, and the accumulator is released right after its last tcgen05.ld.
-        constexpr int MY_SLABS = BN / 128;
+        // Each warp owns WCOLS columns of its 32 rows, in 32-column pieces: tcgen05.ld -> math -> private 64B-swizzled
+        // 2 KB staging slab -> its own TMA bulk store. No CTA-wide barrier: a warp only ever waits for its own previous
+        // store to have drained the slab, and the accumulator is released right after the warp's last tcgen05.ld.
         uint8_t* slab = sC + (warp - 4) * Cfg::SLAB_BYTES;
-        const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
         float2 rn = make_float2(1.f, 0.f);
-        if (LNIN && row < p.M) rn = row_norm_from_stats(p.in_stats, p.K / 64, p.M, row, p.K, p.in_eps);
-        // residual rows are fetched one 32-column piece ahead (the first one before the accumulator is even ready)
+        // residual rows are fetched one piece ahead (the first one before the accumulator is even ready)
         uint4 res_next[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         const bf16* res_row = nullptr;
         if (EPI == EPI_BIAS_RESIDUAL && row < p.M) {
-          res_row = p.residual + static_cast<size_t>(row) * p.ldr + n0;
+          res_row = p.residual + static_cast<size_t>(row) * p.ldr + n0 + part * WCOLS;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row + half * 64)[i];
+          for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row)[i];
+        }
+        if (LNIN) {
+          mbar_wait(&bar_rnfull[as], aphase);
+          rn = s_rn[as * GEMM_BM + row_in_tile];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_rnempty[as]);
         }
         mbar_wait(&bar_tfull[as], aphase);
         tcgen05_fence_after();
-        uint32_t acc[2][32];
         float2 st_carry = make_float2(0.f, 0.f);
-        tmem_ld_32x32(tq + half * 64, acc[0]);
 #pragma unroll
-        for (int pc = 0; pc < 2 * MY_SLABS; ++pc) {  // 32-column pieces; two per slab
-          const int sl = half + 2 * (pc >> 1);
-          const int col_in_tile = sl * 64 + (pc & 1) * 32;
-          tmem_ld_wait();
-          if (pc + 1 < 2 * MY_SLABS) {
-            const int nsl = half + 2 * ((pc + 1) >> 1);
-            tmem_ld_32x32(tq + nsl * 64 + ((pc + 1) & 1) * 32, acc[(pc + 1) & 1]);
-          }
+        for (int pc = 0; pc < PIECES; ++pc) {
+          const int col_in_tile = part * WCOLS + pc * 32;
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + pc * 32, acc);
           uint4 res_cur[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
-          if (EPI == EPI_BIAS_RESIDUAL && res_row != nullptr && pc + 1 < 2 * MY_SLABS) {
-            const int nsl = half + 2 * ((pc + 1) >> 1);
+          if (EPI == EPI_BIAS_RESIDUAL && res_row != nullptr && pc + 1 < PIECES) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              res_next[i] = reinterpret_cast<const uint4*>(res_row + nsl * 64 + ((pc + 1) & 1) * 32)[i];
+            for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row + (pc + 1) * 32)[i];
           }
-          float v[32];
-          epilogue_values<EPI, LNIN>(acc[pc & 1], n0 + col_in_tile, p, rn, res_cur, v);
-          uint4 o[4];
-          pack32(v, o);
-          float2 st_piece = make_float2(0.f, 0.f);
-          if (p.out_stats != nullptr) st_piece = stats32(v);
-          if ((pc & 1) == 0) {
-            // the previous TMA store of this warp must have finished reading the slab before it is refilled
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)  // 128B swizzle: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
-            *reinterpret_cast<uint4*>(slab + lane * 128 + ((((pc & 1) * 4 + i) ^ (lane & 7)) << 4)) = o[i];
-          static_assert(MY_SLABS <= 2, "stats carry below assumes at most two slabs per warp");
-          if (pc & 1) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tmC)),
-                           "r"(smem_u32(slab)), "r"(n0 + sl * 64), "r"(m0 + q * 32)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          }
-          if (p.out_stats != nullptr) {
-            if ((pc & 1) == 0) {
-              st_carry = st_piece;
-            } else if (row < p.M) {
-              reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>((n0 >> 6) + sl) * p.M + row] =
-                  stats_merge(st_carry, st_piece, 32.0f);
-            }
-          }
-          if (pc + 1 == 2 * MY_SLABS) {
-            // every tcgen05.ld of this tile has completed (wait::ld at the top of this iteration): release the accumulator
+          tmem_ld_wait();
+          if (pc + 1 == PIECES) {  // every tcgen05.ld of this warp for this tile has completed: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[as]);
+          }
+          float v[32];
+          epilogue_values<EPI, LNIN>(acc, n0 + col_in_tile, p, rn, res_cur, v);
+          uint4 o[4];
+          pack32(v, o);
+          if (p.out_stats != nullptr) {
+            const float2 st_piece = stats32(v);
+            if (PIECES == 1) {  // 128-wide tiles: 32-column chunks
+              if (row < p.M)
+                reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>((n0 + col_in_tile) >> 5) * p.M + row] = st_piece;
+            } else if (pc == 0) {
+              st_carry = st_piece;
+            } else if (row < p.M) {  // 256-wide tiles: this warp's two pieces form one 64-column chunk
+              reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>((n0 + part * WCOLS) >> 6) * p.M + row] =
+                  stats_merge(st_carry, st_piece, 32.0f);
+            }
+          }
+          // the previous TMA store of this warp must have finished reading the slab before it is refilled
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i)  // 64B swizzle: 16-byte chunk c of 64-byte row r lives at chunk position c ^ ((r >> 1) & 3)
+            *reinterpret_cast<uint4*>(slab + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = o[i];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(smem_u32(slab)), "r"(n0 + col_in_tile), "r"(m0 + q * 32)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       } else if constexpr (sizeof(OutT) == 4) {
         mbar_wait(&bar_tfull[as], aphase);
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < COLS; c += 32) {
+        for (int c = 0; c < WCOLS; c += 32) {
           uint32_t acc[32];
           tmem_ld_32x32(taddr + c, acc);
           tmem_ld_wait();
-          epilogue_chunk<EPI, OutT>(acc, row, n0 + half * COLS + c, p);
+          epilogue_chunk<EPI, OutT>(acc, row, n0 + part * WCOLS + c, p);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -508,7 +572,7 @@ using namespace lrce;
 extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                               const void* residual, int ldr, void* out, int ldo, int epilogue, int out_fp32,
                               const float* ln_gamma, const float* ln_beta, float ln_eps, const float* in_stats,
-                              const float* in_colsum, float in_eps, float* out_stats, void* stream) {
+                              int in_chunk, const float* in_colsum, float in_eps, float* out_stats, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(A && W && out, "lrce_gemm_bf16: null operand");
@@ -521,9 +585,10 @@ extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
     LRCE_REQUIRE(residual && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                  "lrce_gemm_bf16: residual epilogue needs a 16B-aligned residual");
   if (in_stats != nullptr)
-    LRCE_REQUIRE(in_colsum && bias && K % 64 == 0 && K <= 1024 && (reinterpret_cast<uintptr_t>(in_colsum) & 15) == 0 &&
+    LRCE_REQUIRE(in_colsum && bias && (in_chunk == 32 || in_chunk == 64) && K % in_chunk == 0 &&
+                     (K / in_chunk == 4 || K / in_chunk == 8 || K / in_chunk == 16) && (reinterpret_cast<uintptr_t>(in_colsum) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(in_stats) & 7) == 0,
-                 "lrce_gemm_bf16: a folded LayerNorm input needs statistics, column sums, a bias and K %% 64 == 0 (K=%d)", K);
+                 "lrce_gemm_bf16: a folded LayerNorm input needs statistics in 4, 8 or 16 chunks of 32 or 64 columns, column sums and a bias (K=%d, chunk=%d)", K, in_chunk);
   if (out_stats != nullptr)
     LRCE_REQUIRE(!out_fp32 && (reinterpret_cast<uintptr_t>(out_stats) & 7) == 0,
                  "lrce_gemm_bf16: row statistics are emitted for bf16 outputs only");
@@ -535,14 +600,14 @@ extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   p.out = out;
   p.ldo = ldo;
   p.ln_g = ln_gamma; p.ln_b = ln_beta; p.ln_eps = ln_eps;
-  p.in_stats = in_stats; p.in_colsum = in_colsum; p.in_eps = in_eps;
+  p.in_stats = in_stats; p.in_chunk = in_chunk; p.in_colsum = in_colsum; p.in_eps = in_eps;
   p.out_stats = out_stats;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB, tmC;
   rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, GEMM_BK, GEMM_BM);
   if (rc != LRCE_OK) return rc;
-  if (!out_fp32 && epilogue != EPI_BIAS_LN) {  // bf16 tiles leave as per-warp TMA stores of 32-row x 64-column slabs
-    rc = make_tmap_2d_bf16(&tmC, out, N, M, ldo, 64, 32);
+  if (!out_fp32 && epilogue != EPI_BIAS_LN) {  // bf16 tiles leave as per-warp TMA stores of 32-row x 32-column slabs
+    rc = make_tmap_2d_bf16(&tmC, out, N, M, ldo, 32, 32, /*swizzle_bytes=*/64);
     if (rc != LRCE_OK) return rc;
   } else {
     tmC = tmA;  // unused by these epilogues

@@ -15,10 +15,11 @@ int require_sm100();
 // cudaGetLastError() -> LRCE_ECUDA + message
 int check_launch(const char* what);
 
-// 2-D bf16 tensor map with 128-byte swizzle: global tensor [outer][inner] with row pitch ld_elems,
-// box = box_outer x box_inner (box_inner * 2 B must be 128 B for the UMMA SW128 K-major layout).
+// 2-D bf16 tensor map: global tensor [outer][inner] with row pitch ld_elems, box = box_outer x box_inner, smem side
+// swizzled with a 128-byte (UMMA SW128 K-major operand tiles; box_inner * 2 B == 128) or 64-byte (box_inner * 2 B == 64)
+// pattern.
 int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                      uint32_t box_inner, uint32_t box_outer);
+                      uint32_t box_inner, uint32_t box_outer, int swizzle_bytes = 128);
 
 int sm_count();
 

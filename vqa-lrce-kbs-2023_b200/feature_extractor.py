@@ -188,7 +188,7 @@ class SwinTransformer3D(nn.Module):
         M = a.shape[0]
         # per-row LayerNorm partials (mean, M2 per 64-column chunk) travel from each GEMM that writes the residual
         # stream to the next GEMM that reads it through a LayerNorm; two buffers alternate (norm1 / norm2)
-        st_a = torch.empty(M * self.embed_dim // 32, device=a.device, dtype=torch.float32)  # [C/64, M, 2] at any stage
+        st_a = torch.empty(M * self.embed_dim // 16, device=a.device, dtype=torch.float32)  # >= [C/chunk, M, 2] at any stage
         st_b = torch.empty_like(st_a)
         x = ops.gemm(a, pk["pe_w"], pk["pe_b"], epilogue=ops.EPI_BIAS_LN, ln=(pk["pe_g"], pk["pe_beta"], 1e-5), stats_out=st_a)
         if taps is not None:

@@ -51,11 +51,17 @@ def _call(name, *args, work=None):
     trace.append((name, tag, flops, nbytes, e0, e1))
 
 
+def stats_chunk(width):
+    """column width of the LayerNorm partials a GEMM with `width` output features emits (lrce_gemm_bf16 out_stats)"""
+    return 64 if width % 256 == 0 else 32
+
+
 def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, residual=None, out=None, out_fp32=False, ln=None, ln_in=None,
          stats_out=None):
     """out = epilogue(a @ w.T); a (M,K) bf16 with unit inner stride, w (N,K) bf16; see lrce_gemm_bf16.
-    ln_in = (stats fp32 [K/64, M, 2], colsum fp32 [N], eps): LayerNorm folded into the A operand (w, bias pre-folded);
-    stats_out = fp32 [N/64, M, 2] buffer that receives the (mean, M2) partials of the rows written."""
+    ln_in = (stats fp32 [K/cw, M, 2], colsum fp32 [N], eps): LayerNorm folded into the A operand (w, bias pre-folded);
+    stats_out = fp32 [N/cw, M, 2] buffer that receives the (mean, M2) partials of the rows written.
+    cw = stats_chunk(width) of the PRODUCING GEMM: 64 columns when its N % 256 == 0, else 32."""
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(bias, torch.float32, "bias")
     _req(residual, torch.bfloat16, "residual")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
@@ -74,13 +80,13 @@ def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, residual=None, out=None, out_fp3
     if ln_in is not None:
         st_in, cs, eps_in = ln_in
         _req(st_in, torch.float32, "ln_in stats"); _req(cs, torch.float32, "ln_in colsum")
-        assert st_in.is_contiguous() and st_in.numel() >= (K // 64) * M * 2 and cs.numel() == N
+        assert st_in.is_contiguous() and st_in.numel() >= (K // stats_chunk(K)) * M * 2 and cs.numel() == N
     if stats_out is not None:
         _req(stats_out, torch.float32, "stats_out")
-        assert stats_out.is_contiguous() and stats_out.numel() >= (N // 64) * M * 2
+        assert stats_out.is_contiguous() and stats_out.numel() >= (N // stats_chunk(N)) * M * 2
     _call("lrce_gemm_bf16", _ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(bias), _ptr(residual),
           residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), epilogue, int(out_fp32),
-          _ptr(g), _ptr(b), float(eps), _ptr(st_in), _ptr(cs), float(eps_in), _ptr(stats_out), _stream(),
+          _ptr(g), _ptr(b), float(eps), _ptr(st_in), stats_chunk(K), _ptr(cs), float(eps_in), _ptr(stats_out), _stream(),
           work=(f"M{M}N{N}K{K}e{epilogue}", 2.0 * M * N * K,
                 2.0 * (M * K + N * K + M * N * (2 if residual is not None else 1)) * (2 if out_fp32 else 1)))
     return out

@@ -122,25 +122,24 @@ int lrce_text_posembed_ln(const void* text, int text_fp32, const float* emb_cls,
 #define LRCE_ACT_GELU 1
 #define LRCE_ACT_RELU 2
 
-/* Y[rows, N] (pitch ldy; fp32, or bf16 when y_bf16 != 0) = act(X W^T + bias) with X = Xa (+ Xb), optionally
- * LayerNorm'ed (ln_gamma != NULL, K == 768; the normalised X is also written to Xout fp32 when non-NULL). Xa is fp32
- * [rows, K], or bf16 when xa_bf16 != 0 (then Xb and ln_gamma must be NULL); K in {768, 3072}; W bf16 with
- * ceil(N/8)*8 rows of K. The summarisation-token path of nn.TransformerDecoderLayer (post-norm) and final_fc:
- * replaces fusionv3.py:46 (per-layer linears + norms on the 1-token target) and :195. */
-int lrce_skinny_linear(const void* Xa, int xa_bf16, const float* Xb, const float* ln_gamma, const float* ln_beta, float eps,
-                       float* Xout, const void* W, const float* bias, void* Y, int y_bf16, int rows, int K, int N, int ldy,
-                       int act, void* stream);
-
-/* ctx[rows, 768] (bf16) = softmax(q K^T) V for one query token per row over the memory [video segment `seg` (Tv tokens) ; text
- * (Lt tokens)], 12 heads x 64; q fp32 already scaled by 1/8. kv_video bf16 [(rows/n_cand)*S*Tv, ld_kv], kv_text bf16
- * [rows*Lt, ld_kv], K at column layer*1536 + head*64, V at +768. Replaces the multihead_attn call inside
- * nn.TransformerDecoderLayer (fusionv3.py:45-46; candidate expansion fusionv3.py:259). */
-int lrce_cross_attention(const float* q, const void* kv_video, const void* kv_text, void* ctx, int rows, int seg, int S,
-                         int Tv, int Lt, int n_cand, int layer, int ld_kv, void* stream);
-
-/* tok_out = LN_f(tok + LN_3(h + y)): closes the 12th decoder layer and the recurrent step (fusionv3.py:47-48). */
-int lrce_recurrent_update(const float* tok, const float* h, const float* y, const float* g3, const float* b3,
-                          const float* gf, const float* bf, float eps, float* tok_out, int rows, void* stream);
+/* The whole summarisation-token walk of FusionTransformer.forward (fusionv3.py:41-51) plus final_fc (:195, ReLU :368) as
+ * ONE persistent cooperative kernel: S segments x n_layers post-norm decoder layers on `rows` tokens, phases separated by
+ * grid-wide barriers. `layer_table` is a DEVICE array of n_layers records of 16 device pointers each, in this order:
+ *   bf16 sa_w[768,768] (out_proj . v_proj of the length-1 self-attention, folded), q_w[768,768] (pre-scaled by 1/8),
+ *   o_w[768,768], w1[3072,768], w2[768,3072]; fp32 sa_b, q_b, o_b, b1, b2, norm1 g/b, norm2 g/b, norm3 g/b.
+ * kv_video bf16 [(rows/n_cand)*S*Tv, ld_kv], kv_text bf16 [rows*Lt, ld_kv] hold K at column layer*1536 + head*64 and V at
+ * +768 (one lrce_gemm_bf16 per modality). tok0 fp32 [768] = summarization_token; f_gamma/f_beta = fusion_layer_norm;
+ * fc_w bf16 [ceil(n_out/8)*8, 768]; act = LRCE_ACT_*; out fp32 [rows, n_out]; tokens_tap NULL or fp32 [S, rows, 768]
+ * (the token after each segment). `workspace`: lrce_encoder_walk_workspace_bytes(rows) bytes, 256-byte aligned, contents
+ * don't matter. Tv + Lt <= 256. */
+size_t lrce_encoder_walk_workspace_bytes(int rows);
+/* profiling hook: the last CTA of later lrce_encoder_walk launches writes %globaltimer three times per phase (after its
+ * prologue, before and after the grid barrier) into buf (device, >= 3 + 18 * S * n_layers entries); NULL switches it off. */
+int lrce_debug_walk_timing(unsigned long long* buf);
+int lrce_encoder_walk(const void* layer_table, int n_layers, const void* kv_video, const void* kv_text, int ld_kv,
+                      const float* tok0, const float* f_gamma, const float* f_beta, float eps, const void* fc_w,
+                      const float* fc_b, int n_out, int act, float* out, float* tokens_tap, void* workspace, int rows, int S,
+                      int Tv, int Lt, int n_cand, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,14 +1,24 @@
-"""GPU probe: per-launch timing of the recurrent encoder's kernels by shape tag."""
-import sys, os, collections
+"""GPU probe: timing of the encoder (K/V GEMMs + persistent token walk) and, through the lrce_debug_walk_timing hook,
+the per-phase breakdown of the walk kernel as seen by CTA 0 (work time vs grid-barrier wait per phase)."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
 import lrce_b200
-from lrce_b200 import ops
+from lrce_b200 import _lib, ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-m = lrce_b200.LRCEOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [3], 32).cuda().eval()
-vf = torch.randn(B, 3, 3, 49, 1024, device="cuda").bfloat16()
-tf = torch.randn(B, 32, 768, device="cuda")
+kind = sys.argv[2] if len(sys.argv) > 2 else "oe"
+S = 3
+if kind == "mc":
+    m = lrce_b200.LRCEMultipleChoice(768, 1, 0.1, [7, 7], 1024, 5, [S], 40).cuda().eval()
+    tf = torch.randn(B, 5, 40, 768, device="cuda")
+else:
+    m = lrce_b200.LRCEOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [S], 32).cuda().eval()
+    tf = torch.randn(B, 32, 768, device="cuda")
+vf = torch.randn(B, S, 3, 49, 1024, device="cuda").bfloat16()
 with torch.no_grad():
     for _ in range(3):
         m(vf, tf)
@@ -18,15 +28,31 @@ with torch.no_grad():
     for _ in range(5):
         m(vf, tf)
     e1.record(); torch.cuda.synchronize()
-    print(f"encoder forward B={B}: {e0.elapsed_time(e1)/5:.3f} ms")
+    print(f"encoder forward B={B} {kind}: {e0.elapsed_time(e1)/5:.3f} ms")
     ops.trace = []
     m(vf, tf)
     torch.cuda.synchronize()
     tr, ops.trace = ops.trace, None
-agg = collections.OrderedDict()
-for i, (name, tag, fl, by, a, b) in enumerate(tr):
-    key = (name, tag) if name != "lrce_skinny_linear" else (name, f"call{(i - 5) % 6 if i >= 5 else i}")
-    d = agg.setdefault(key, [0.0, 0])
-    d[0] += a.elapsed_time(b); d[1] += 1
-for k, (ms, n) in agg.items():
-    print(f"{k[0]:28s} {k[1]:24s} n={n:4d} avg {ms/n*1e3:8.1f} us total {ms:7.3f} ms")
+    for name, tag, fl, by, a, b in tr:
+        print(f"  {name:28s} {tag:24s} {a.elapsed_time(b)*1e3:8.1f} us")
+    n = 3 + 18 * S * 12
+    buf = torch.zeros(n, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().lrce_debug_walk_timing(buf.data_ptr()), "timing hook")
+    m(vf, tf)
+    torch.cuda.synchronize()
+    _lib.lib().lrce_debug_walk_timing(0)
+t = buf.cpu().tolist()
+names = ["P1 self", "P2 q", "P3 attn", "P4 out", "P5 fc1", "P6 fc2"]
+pro, work, wait = [0.0] * 6, [0.0] * 6, [0.0] * 6
+# stamps: [start] then per phase (after prologue / staging, before barrier, after barrier)
+for i in range(S * 12 * 6):
+    prev = t[3 * i]  # after the previous barrier (or kernel start)
+    a, done, released = t[3 * i + 1], t[3 * i + 2], t[3 * i + 3]
+    pro[i % 6] += a - prev
+    work[i % 6] += done - a
+    wait[i % 6] += released - done
+k = S * 12
+for j in range(6):
+    print(f"  {names[j]:8s} prologue {pro[j]/k/1e3:6.2f} us  tiles {work[j]/k/1e3:6.2f} us  barrier wait {wait[j]/k/1e3:6.2f} us"
+          f"   (CTA 1, mean over {k} layer-steps)")
+print(f"  head     {(t[-1]-t[-3])/1e3:7.2f} us ; whole walk {(t[-1]-t[0])/1e3:8.1f} us")

@@ -93,16 +93,12 @@ if which in ("rows", "all"):
         order.append(f"patch_merge_ln C{C}")
 
 if which in ("enc", "all"):
-    os.environ["LRCE_B200_NO_GRAPH"] = "1"
-    from lrce_b200 import fusion
-
-    fusion._NO_GRAPH = True
     m = lrce_b200.LRCEOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [1], 32).cuda().eval()  # S=1: one recurrent step
     vf = rnd(32, 1, 3, 49, 1024)
     tf = torch.randn(32, 32, 768, device=dev)
     with torch.no_grad():
         m(vf, tf)
     torch.cuda.synchronize()
-    order.append("encoder S=1 forward (12 layer-steps, kernel by kernel)")
+    order.append("encoder S=1 forward (K/V GEMMs + one persistent walk kernel)")
 
 print("\n".join(order))

@@ -27,11 +27,11 @@ _SIGNATURES = {
     "lrce_window_attention_bf16": [_vp, _vp, _vp] + [_i] * 8 + [_vp],
     "lrce_video_posembed_ln": [_vp] * 7 + [_f, _vp, _i, _i, _i, _i, _vp],
     "lrce_text_posembed_ln": [_vp, _i] + [_vp] * 4 + [_f, _vp, _i, _i, _vp],
-    "lrce_skinny_linear": [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "lrce_cross_attention": [_vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
-    "lrce_recurrent_update": [_vp] * 7 + [_f, _vp, _i, _vp],
+    "lrce_encoder_walk_workspace_bytes": [_i],
+    "lrce_debug_walk_timing": [_vp],
+    "lrce_encoder_walk": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
-_RESTYPES = {"lrce_last_error": _c.c_char_p}
+_RESTYPES = {"lrce_last_error": _c.c_char_p, "lrce_encoder_walk_workspace_bytes": _c.c_size_t}
 
 _lib = None
 

@@ -7,10 +7,10 @@ Execution plan of one forward (eval semantics — dropouts are identities, fusio
   3. K/V in-projections of ALL 12 decoder layers for every memory token in ONE GEMM per modality
      ([Wk;Wv] of the 12 layers concatenated -> N = 18432). Text rows are projected once, not once per segment, and for
      multiple choice the video rows are projected once per clip, not once per candidate (fusionv3.py:259 expands them).
-  4. the summarisation token: S x 12 layer-steps of 6 small kernels (see csrc/encoder.cu). Self-attention over a
-     length-1 target is softmax over a single key = 1, so it reduces to out_proj(v_proj(x)); the two matrices are
-     folded into one 768x768 product at pack time.
-  5. final_fc as one more skinny linear (ReLU fused for the counting head, fusionv3.py:368).
+  4. the summarisation token: S x 12 layer-steps of 6 dependent sub-steps plus final_fc (ReLU fused for the counting
+     head, fusionv3.py:368) run as ONE persistent cooperative kernel with grid-wide barriers between sub-steps (see
+     csrc/encoder_walk.cu). Self-attention over a length-1 target is softmax over a single key = 1, so it reduces to
+     out_proj(v_proj(x)); the two matrices are folded into one 768x768 product at pack time.
 """
 from typing import Iterable, List
 
@@ -20,10 +20,7 @@ from torch import nn
 from . import ops
 from .feature_extractor import _PackedWeights
 
-import os
-
 EPS = 1e-12  # fusionv3.py:14,18 ; embedding.py:15,45
-_NO_GRAPH = os.environ.get("LRCE_B200_NO_GRAPH", "0") == "1"  # debugging aid: launch the token walk kernel by kernel
 
 
 def init_weight(size):
@@ -93,7 +90,7 @@ class LRCEOpenEnded(nn.Module):
         if self._packed.sig != sig:
             self._packed.data = self._pack()
             self._packed.sig = sig
-            self._states = {}  # captured graphs hold pointers into the previous pack
+            self._states = {}
         return self._packed.data
 
     @torch.no_grad()
@@ -138,6 +135,11 @@ class LRCEOpenEnded(nn.Module):
             kv_w.append(ca_w[d:])
             kv_b.append(ca_b[d:])
         pk["kv_w"], pk["kv_b"] = bf(torch.cat(kv_w)), f32(torch.cat(kv_b))  # [12*1536, 768]: layer-major, [k | v]
+        # device table of per-layer pointers in the order lrce_encoder_walk documents (include/lrce_b200.h)
+        order = ("sa_w", "q_w", "o_w", "w1", "w2", "sa_b", "q_b", "o_b", "b1", "b2")
+        rows = [[lw[k].data_ptr() for k in order] + [t.data_ptr() for n in ("n1", "n2", "n3") for t in lw[n]]
+                for lw in pk["layers"]]
+        pk["layer_table"] = torch.tensor(rows, dtype=torch.int64, device=dev)
         return pk
 
     # -------------------------------------------------------------------------------------------------------------
@@ -158,72 +160,30 @@ class LRCEOpenEnded(nn.Module):
         if taps is not None:
             taps["video_embedded"], taps["text_embedded"] = vemb, temb
         n_out = self.final_fc.out_features
-        st = self._token_state(pk, dev, B, Bq, S, Tv, Lt, n_cand, act, n_out)
+        st = self._token_state(pk, dev, B, Bq, S, Tv, Lt)
         ops.gemm(vemb.view(B * S * Tv, d), pk["kv_w"], pk["kv_b"], out=st["kv_video"])
         ops.gemm(temb.view(Bq * Lt, d), pk["kv_w"], pk["kv_b"], out=st["kv_text"])
-        use_graph = taps is None and not _NO_GRAPH
-        if use_graph and st["graph"] is None:
-            # the token walk is ~220 tiny dependent launches: capture it once per shape and replay it as one graph launch
-            trace, ops.trace = ops.trace, None
-            try:
-                self._token_walk(pk, st, S, Tv, Lt, n_cand, act, None)  # eager warm-up (sets kernel attributes)
-                n0 = ops.launches
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    self._token_walk(pk, st, S, Tv, Lt, n_cand, act, None)
-                st["graph"], st["graph_launches"] = graph, ops.launches - n0
-            finally:
-                ops.trace = trace
-        if use_graph:
-            st["graph"].replay()
-            ops.launches += st["graph_launches"]
-        else:
-            self._token_walk(pk, st, S, Tv, Lt, n_cand, act, taps)
-        return st["out"].clone()
+        out = torch.empty((Bq, n_out), device=dev, dtype=torch.float32)
+        tap = torch.empty((S, Bq, d), device=dev, dtype=torch.float32) if taps is not None else None
+        ops.encoder_walk(pk["layer_table"], len(pk["layers"]), st["kv_video"], st["kv_text"], pk["tok"], pk["f_g"], pk["f_b"],
+                         EPS, pk["fc_w"], pk["fc_b"], n_out, act, out, st["ws"], Bq, S, Tv, Lt, n_cand, tokens_tap=tap)
+        if taps is not None:
+            for s in range(S):
+                taps[f"token.s{s}"] = tap[s]
+        return out
 
-    def _token_state(self, pk, dev, B, Bq, S, Tv, Lt, n_cand, act, n_out):
-        """static buffers (and the captured graph) of the token walk for one problem shape and one weight pack"""
-        key = (id(pk), dev, B, Bq, S, Tv, Lt, n_cand, act)
+    def _token_state(self, pk, dev, B, Bq, S, Tv, Lt):
+        """K/V buffers and the walk's workspace for one problem shape (reused across forwards)"""
+        key = (dev, B, Bq, S, Tv, Lt)
         st = self._states.get(key)
         if st is None:
             if len(self._states) > 8:
                 self._states.clear()
-            d = self.feature_dim
-            f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
             h = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
             st = dict(kv_video=h(B * S * Tv, pk["kv_w"].shape[0]), kv_text=h(Bq * Lt, pk["kv_w"].shape[0]),
-                      tok0=pk["tok"].expand(Bq, d).contiguous(), tok_a=f(Bq, d), tok_b=f(Bq, d), h=f(Bq, d), h1=f(Bq, d),
-                      h2=f(Bq, d), y=f(Bq, d), q=f(Bq, d), yo=f(Bq, d), yf=f(Bq, d),
-                      ctx=h(Bq, d), hdn=h(Bq, 4 * d),  # bf16 hand-offs feed the next kernel's A operand directly
-                      out=f(Bq, n_out), graph=None, graph_launches=0)
+                      ws=ops.encoder_walk_workspace(Bq, dev))
             self._states[key] = st
         return st
-
-    def _token_walk(self, pk, st, S, Tv, Lt, n_cand, act, taps):
-        d = self.feature_dim
-        layers = pk["layers"]
-        kv_video, kv_text = st["kv_video"], st["kv_text"]
-        h, h1, h2, y, q, ctx, yo, yf, hdn = (st[k] for k in ("h", "h1", "h2", "y", "q", "ctx", "yo", "yf", "hdn"))
-        tok, bufs = st["tok0"], [st["tok_a"], st["tok_b"]]
-        for s in range(S):
-            for n, lw in enumerate(layers):
-                if n == 0:
-                    cur = tok
-                    ops.skinny_linear(tok, lw["sa_w"], lw["sa_b"], y, d)
-                else:  # cur = LN3_{n-1}(h2 + yf), materialised into h by the kernel's first CTA column
-                    cur = h
-                    ops.skinny_linear(h2, lw["sa_w"], lw["sa_b"], y, d, xb=yf, ln=layers[n - 1]["n3"], xout=h)
-                ops.skinny_linear(cur, lw["q_w"], lw["q_b"], q, d, xb=y, ln=lw["n1"], xout=h1)
-                ops.cross_attention(q, kv_video, kv_text, ctx, s, S, Tv, Lt, n_cand, n)
-                ops.skinny_linear(ctx, lw["o_w"], lw["o_b"], yo, d)
-                ops.skinny_linear(h1, lw["w1"], lw["b1"], hdn, 4 * d, xb=yo, ln=lw["n2"], xout=h2, act=ops.ACT_GELU)
-                ops.skinny_linear(hdn, lw["w2"], lw["b2"], yf, d)
-            nxt = bufs[s & 1]
-            ops.recurrent_update(tok, h2, yf, layers[-1]["n3"][0], layers[-1]["n3"][1], pk["f_g"], pk["f_b"], EPS, nxt)
-            tok = nxt
-            if taps is not None:
-                taps[f"token.s{s}"] = tok.clone()
-        ops.skinny_linear(tok, pk["fc_w"], pk["fc_b"], st["out"], st["out"].shape[1], act=act)
 
     def forward(self, video_features, text_features, texts_attention_mask=None, taps=None):
         """(B, S, T, 49, Dv), (B, L, 768) -> (B, num_classes) fp32 (fusionv3.py:168-198). `texts_attention_mask` is

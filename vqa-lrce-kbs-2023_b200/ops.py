@@ -191,33 +191,26 @@ def text_posembed_ln(text, emb_cls, emb_pos, gamma, beta, eps):
     return out
 
 
-def skinny_linear(xa, w, bias, out, n_out, *, xb=None, ln=None, xout=None, act=ACT_NONE, eps=1e-12):
-    """out[rows, n_out] (fp32 or bf16) = act(LN?(xa + xb) @ w.T + bias); xa fp32 or bf16; w bf16 [ceil(n_out/8)*8, K]."""
-    _req(xb, torch.float32, "xb"); _req(w, torch.bfloat16, "w"); _req(xout, torch.float32, "xout")
-    if xa.dtype not in (torch.float32, torch.bfloat16) or out.dtype not in (torch.float32, torch.bfloat16):
-        raise _lib.LrceError("skinny_linear: xa / out must be fp32 or bf16")
-    _req(xa, xa.dtype, "xa"); _req(out, out.dtype, "out")
-    rows, K = xa.shape
-    assert xa.is_contiguous() and w.is_contiguous() and w.shape[1] == K and w.shape[0] >= n_out and w.shape[0] % 8 == 0
-    assert out.stride(1) == 1 and out.shape[0] == rows
-    g, b = ln if ln is not None else (None, None)
-    _call("lrce_skinny_linear", _ptr(xa), int(xa.dtype == torch.bfloat16), _ptr(xb), _ptr(g), _ptr(b), float(eps),
-          _ptr(xout), _ptr(w), _ptr(bias), _ptr(out), int(out.dtype == torch.bfloat16), rows, K, n_out, out.stride(0),
-          act, _stream(), work=(f"K{K}N{n_out}", 2.0 * rows * K * n_out, 2.0 * K * n_out))
-    return out
+def encoder_walk_workspace(rows, device):
+    """scratch for encoder_walk (contents don't matter; the library zeroes its barrier word itself)"""
+    n = _lib.lib().lrce_encoder_walk_workspace_bytes(int(rows))
+    return torch.empty((n + 255) // 256 * 256, device=device, dtype=torch.uint8)
 
 
-def cross_attention(q, kv_video, kv_text, ctx, seg, S, Tv, Lt, n_cand, layer):
-    _req(q, torch.float32, "q"); _req(kv_video, torch.bfloat16, "kv_video"); _req(kv_text, torch.bfloat16, "kv_text")
-    _req(ctx, torch.bfloat16, "ctx")
-    rows = q.shape[0]
-    assert kv_video.stride(0) == kv_text.stride(0)
-    _call("lrce_cross_attention", _ptr(q), _ptr(kv_video), _ptr(kv_text), _ptr(ctx), rows, seg, S, Tv, Lt, n_cand, layer,
-          kv_video.stride(0), _stream())
-    return ctx
-
-
-def recurrent_update(tok, h, y, g3, b3, gf, bf, eps, out):
-    _call("lrce_recurrent_update", _ptr(tok), _ptr(h), _ptr(y), _ptr(g3), _ptr(b3), _ptr(gf), _ptr(bf), float(eps),
-          _ptr(out), tok.shape[0], _stream())
+def encoder_walk(layer_table, n_layers, kv_video, kv_text, tok0, f_g, f_b, eps, fc_w, fc_b, n_out, act, out, workspace, rows,
+                 S, Tv, Lt, n_cand, tokens_tap=None):
+    """the whole summarisation-token walk + answer head as one persistent cooperative kernel (lrce_encoder_walk)"""
+    _req(kv_video, torch.bfloat16, "kv_video"); _req(kv_text, torch.bfloat16, "kv_text"); _req(fc_w, torch.bfloat16, "fc_w")
+    _req(tok0, torch.float32, "tok0"); _req(out, torch.float32, "out"); _req(tokens_tap, torch.float32, "tokens_tap")
+    assert layer_table.dtype == torch.int64 and layer_table.is_cuda and layer_table.shape == (n_layers, 16)
+    assert kv_video.stride(0) == kv_text.stride(0) and out.is_contiguous() and out.shape == (rows, n_out)
+    assert fc_w.shape[0] % 8 == 0 and fc_w.shape[0] >= n_out and fc_w.shape[1] == 768
+    assert workspace.data_ptr() % 256 == 0 and workspace.numel() >= _lib.lib().lrce_encoder_walk_workspace_bytes(int(rows))
+    if tokens_tap is not None:
+        assert tokens_tap.is_contiguous() and tokens_tap.shape == (S, rows, 768)
+    _call("lrce_encoder_walk", _ptr(layer_table), n_layers, _ptr(kv_video), _ptr(kv_text), kv_video.stride(0), _ptr(tok0),
+          _ptr(f_g), _ptr(f_b), float(eps), _ptr(fc_w), _ptr(fc_b), n_out, act, _ptr(out), _ptr(tokens_tap), _ptr(workspace),
+          rows, S, Tv, Lt, n_cand, _stream(),
+          work=(f"R{rows}S{S}", 2.0 * rows * S * n_layers * (4 * 768 * 768 + 2 * 768 * 3072 + 2 * (Tv + Lt) * 768),
+                2.0 * S * n_layers * (3 * 768 * 768 + 2 * 768 * 3072) + 2.0 * rows * S * n_layers * (Tv + Lt) * 1536 * 2))
     return out

@@ -65,6 +65,14 @@ if which == "pick":  # the few launches worth an `ncu --set full --import-source
     torch.cuda.synchronize()
     order.append("attn s3 shift(3,3)")
 
+if which == "attn1":  # one stage-3 shifted attention launch (for ncu --set full --import-source on)
+    qkv = rnd(N_SEG * 588, 1536)
+    bias = ops.window_bias_pack(torch.randn(2535, 16, device=dev) * 0.5)
+    torch.cuda.synchronize()
+    ops.window_attention(qkv, bias, N_SEG, 3, 14, 14, 512, 16, (3, 3))
+    torch.cuda.synchronize()
+    order.append("attn s3 shift(3,3)")
+
 if which in ("attn", "all"):
     for name, hw, C, heads in [("s1", 56, 128, 4), ("s2", 28, 256, 8), ("s3", 14, 512, 16), ("s4", 7, 1024, 32)]:
         T = 3 * hw * hw

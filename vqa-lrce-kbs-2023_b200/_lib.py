@@ -29,6 +29,7 @@ _SIGNATURES = {
     "lrce_text_posembed_ln": [_vp, _i] + [_vp] * 4 + [_f, _vp, _i, _i, _vp],
     "lrce_encoder_walk_workspace_bytes": [_i],
     "lrce_debug_walk_timing": [_vp],
+    "lrce_debug_attention_timing": [_vp],
     "lrce_encoder_walk": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"lrce_last_error": _c.c_char_p, "lrce_encoder_walk_workspace_bytes": _c.c_size_t}

@@ -33,6 +33,41 @@ __host__ __device__ inline int window_source_token(const StageGeom& g, int win, 
   return (sd_ * g.H + sh_) * g.W + sw_;
 }
 
+// The same map specialised for LRCE's clamped (3,7,7) window on a D == 3 grid (every Swin stage of the path): constant
+// divisors and a conditional subtract instead of ~10 integer divisions per token. (hW, wW) are the window's coordinates
+// in the window grid: wW = win % (W/7), hW = (win / (W/7)) % (H/7). lrce_remap_index() and the standalone remap kernel
+// use this function whenever the geometry allows, so the bit-exact tests pin exactly what the attention kernel executes.
+__host__ __device__ inline bool is_window_377(const StageGeom& g) {
+  return g.D == 3 && g.wd == 3 && g.wh == 7 && g.ww == 7 && g.sd == 0;
+}
+__host__ __device__ inline int window_source_token_377(const StageGeom& g, int hW, int wW, int tok) {
+  const int d = tok / 49, rem = tok - d * 49, h = rem / 7, w = rem - h * 7;
+  int y = hW * 7 + h + g.sh, x = wW * 7 + w + g.sw;  // shift < window <= extent: one wrap at most
+  if (y >= g.H) y -= g.H;
+  if (x >= g.W) x -= g.W;
+  return (d * g.H + y) * g.W + x;
+}
+
+// Key order inside the attention kernel's score tile for the (3,7,7) window. Keys are grouped by their shift-mask class
+// k = 2 [h >= 4] + [w >= 4] (the seam of a shift-3 border window, see shift_region_id) so that the mask is constant over
+// every 8-column group of the tile: class 0 -> columns [0, 48), class 1 -> [48, 84) (+4 pads), class 2 -> [88, 124)
+// (+4 pads), class 3 -> [128, 155) (+5 pads). Softmax and P v are invariant to the key order; only K/V staging rows and
+// the dense bias table's columns use it.
+__host__ __device__ inline int key_class_377(int tok) {
+  const int rem = tok % 49, h = rem / 7, w = rem - h * 7;
+  return (h >= 4 ? 2 : 0) + (w >= 4 ? 1 : 0);
+}
+__host__ __device__ inline int key_slot_377(int tok) {
+  const int d = tok / 49, rem = tok - d * 49, h = rem / 7, w = rem - h * 7;
+  const bool ch = h >= 4, cw = w >= 4;
+  const int nh_c = ch ? 3 : 4, nw_c = cw ? 3 : 4;
+  const int idx = (d * nh_c + (ch ? h - 4 : h)) * nw_c + (cw ? w - 4 : w);
+  const int base = ch ? (cw ? 128 : 88) : (cw ? 48 : 0);
+  return base + idx;
+}
+// mask class of the 8-column group `grp` (0..19) of the score tile
+__host__ __device__ inline int key_group_class_377(int grp) { return (grp >= 6) + (grp >= 11) + (grp >= 16); }
+
 // region id (0..8) of token `tok` of window `win` in shifted coordinates; tokens attend each other iff ids are equal.
 // Along a shifted axis of length L the slices [0, L-win), [L-win, L-shift), [L-shift, L) carry ids 0, 1, 2.
 __host__ __device__ inline int shift_region_id(const StageGeom& g, int win, int tok) {

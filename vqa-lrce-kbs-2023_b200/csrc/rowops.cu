@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(256) window_remap_kernel(const bf16* __restric
   const int tok = static_cast<int>(wrow % N);
   const int win = static_cast<int>((wrow / N) % nwin);
   const long long seg = wrow / (static_cast<long long>(N) * nwin);
-  const long long nrow = seg * (static_cast<long long>(g.D) * g.H * g.W) + window_source_token(g, win, tok);
+  const int nw_ = g.W / g.ww, nh_ = g.H / g.wh;
+  const int src_tok = is_window_377(g) ? window_source_token_377(g, (win / nw_) % nh_, win % nw_, tok) : window_source_token(g, win, tok);
+  const long long nrow = seg * (static_cast<long long>(g.D) * g.H * g.W) + src_tok;
   const uint4* src = reinterpret_cast<const uint4*>(in + (SCATTER ? wrow : nrow) * C) + ch;
   uint4* dst = reinterpret_cast<uint4*>(out + (SCATTER ? nrow : wrow) * C) + ch;
   *dst = __ldg(src);
@@ -197,7 +199,10 @@ __global__ void remap_index_kernel(int* __restrict__ gather, int* __restrict__ r
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nwin * N) return;
   const int win = idx / N, tok = idx % N;
-  if (gather) gather[idx] = window_source_token(g, win, tok);
+  if (gather) {
+    const int nw_ = g.W / g.ww, nh_ = g.H / g.wh;
+    gather[idx] = is_window_377(g) ? window_source_token_377(g, (win / nw_) % nh_, win % nw_, tok) : window_source_token(g, win, tok);
+  }
   if (region) region[idx] = shift_region_id(g, win, tok);
   if (relpos && win == 0) relpos[tok] = rel_pos_offset(g, tok);
 }

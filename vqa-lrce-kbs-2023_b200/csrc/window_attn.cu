@@ -8,21 +8,25 @@
 //          roll(window_reverse(attn @ v), +shift) — the proj GEMM + residual then runs with no remap at all.
 //
 // One persistent CTA per SM walks a contiguous range of (head, segment, window) work units; 14 warps:
-//   warps 9,10,13 loaders: one warp each for q, k and v: gather the window's 147 rows (64 B each) from their rolled
-//                          source tokens with 16-byte cp.async (4 lanes per row -> full 32-byte sectors) into UMMA
-//                          "core matrix" order (8 rows x 16 B contiguous), double-buffered; q/k buffers are recycled
-//                          as soon as S has been computed, v buffers after P v; the row index is
-//                          window_source_token(), the function lrce_remap_index() exports for the bit-exact test
-//   warp  11     MMA     : one thread issues S = q k^T (2 row tiles x [M=128, N=160, K=32]) and O = P v (2 x [M=128,
-//                          N=32, K=160], v consumed MN-major exactly as it sits in memory) with tcgen05.mma into TMEM
-//   warps 0-8,12 softmax : thread-per-row on the TMEM accumulator (two warps split the 160 columns of each 32-row
-//                          quarter): t = s*scale*log2e + bias (dense 147x152 bf16 table of this head, resident in
-//                          smem) + shift mask (-100 where region ids differ, video_swin_ori.py:357-358); row max;
-//                          p = exp2(t - max) written as bf16 A-operand tiles to smem; 1/rowsum applied to O in the
-//                          epilogue, which scatters 32-byte row pieces through the inverse remap.
-// S(i+1) and P v(i) run on the tensor core while the softmax warps are still busy with item i's epilogue / item i+1's
-// first pass, so the kernel is bound by the softmax ALU work, not by the MMAs. N = 147 is padded to 2 x 128 query rows
-// and 160 key columns; padded keys get p = 0, padded rows are never stored.
+//   warp  10     loader   : gathers the window's 147 q, k and v rows (64 B each) from their rolled source tokens with
+//                           16-byte cp.async into UMMA "core matrix" order (8 rows x 16 B contiguous), double-buffered;
+//                           the row index is window_source_token_377(), the function lrce_remap_index() exports for the
+//                           bit-exact test. v rows carry a 5th 16-byte chunk holding a constant 1 so that the P v product
+//                           also yields the softmax row sums.
+//   warp  11     MMA      : one thread issues S = q k^T (2 row tiles x [M=128, N=160, K=32]) and, per row tile, TWO
+//                           products O_A = P[:, 0:80] v[0:80], O_B = P[:, 80:160] v[80:160] ([M=128, N=48, K=80], v consumed
+//                           MN-major exactly as it sits in memory) with tcgen05.mma into TMEM
+//   warps 0-7    softmax  : rows 0..127 of the window (thread = row, warp w and w+4 split the 160 key columns in halves)
+//   warps 8,12 / 9,13     : rows 128..146 of even / odd work units (placed in TMEM lane quarter 0 / 1 so that the extra
+//                           load is spread over two warp schedulers)
+// Softmax on the TMEM accumulator: t = s*scale*log2e + bias (dense 147x152 bf16 table of this head, resident in smem)
+// + shift mask (-100 where region ids differ, video_swin_ori.py:357-358; keys are staged grouped by their mask class —
+// remap.cuh key_slot_377 — so the mask is one additive constant per 8-column group of the tile);
+// p = exp2(t - m_half) with the maximum of the thread's OWN 80 columns — the two halves never synchronise: their
+// products are kept in separate accumulators and merged in the epilogue, out = (a O_A + b O_B) / (a l_A + b l_B),
+// a = 2^(m_A - m), b = 2^(m_B - m), l = the ones-column sums. The S accumulator is released as soon as a warp has loaded
+// its 80 scores into registers, so S(i+1) runs on the tensor core under the softmax of item i. All twelve softmax warps
+// execute ONE copy of the (fully unrolled) code: four template instances thrashed the instruction cache.
 #include "host_common.h"
 #include "lrce_common.cuh"
 #include "remap.cuh"
@@ -31,30 +35,31 @@ namespace lrce {
 
 constexpr int WA_N = 147;           // tokens per (3,7,7) window
 constexpr int WA_KEYS = 160;        // key columns of the S tile (multiple of 16)
-constexpr int WA_BIAS_PITCH = 152;  // dense bias row pitch (bf16)
+constexpr int WA_HALF = 80;         // key columns per softmax thread
+constexpr int WA_BIAS_PITCH = 160;  // dense bias row pitch (bf16) = key columns of the score tile
+constexpr int WA_VCH = 6;           // 16-byte chunks per staged v row: 4 of data, 1 with the constant 1, 1 of zeros
+constexpr int WA_ON = 8 * WA_VCH;   // N of the P v products (48)
 constexpr int WA_THREADS = 14 * 32;
+constexpr int WA_SOFTMAX_ARRIVALS = 12;  // 8 main warps + 2 leftover warps of the item + 2 leftover warps of the other parity
 
 // shared memory map (bytes)
 constexpr int WA_Q_BYTES = 256 * 64;  // 2 row tiles x 128 rows x 32 dims
-constexpr int WA_K_BYTES = 160 * 64;
-constexpr int WA_V_BYTES = 160 * 64;
-constexpr int WA_QKV_BYTES = WA_Q_BYTES + WA_K_BYTES + WA_V_BYTES;  // 36864 per buffer
+constexpr int WA_K_BYTES = WA_KEYS * 64;
+constexpr int WA_V_BYTES = WA_KEYS * 16 * WA_VCH;
+constexpr int WA_QKV_BYTES = WA_Q_BYTES + WA_K_BYTES + WA_V_BYTES;  // 41984 per buffer
 constexpr int WA_P_TILE_BYTES = 128 * WA_KEYS * 2;                  // 40960 per row tile
 constexpr int WA_BIAS_BYTES = ((WA_N * WA_BIAS_PITCH * 2 + 127) / 128) * 128;
 constexpr int WA_OFF_QKV = 0;
 constexpr int WA_OFF_P = 2 * WA_QKV_BYTES;
 constexpr int WA_OFF_BIAS = WA_OFF_P + 2 * WA_P_TILE_BYTES;
-// token / region tables are a 4-deep ring (slot = item & 3): the q loader refills a slot as soon as S(item - 2) has been
-// issued, while the softmax warps of item - 2 are still reading theirs
-constexpr int WA_RING = 4;
-constexpr int WA_OFF_TOK = WA_OFF_BIAS + WA_BIAS_BYTES;         // int [3 loaders][WA_RING][160]
-constexpr int WA_OFF_RID = WA_OFF_TOK + 3 * WA_RING * 160 * 4;  // uint8 [WA_RING][160]
-constexpr int WA_OFF_XCHG = WA_OFF_RID + WA_RING * 160;         // float [2 kinds][2 halves][160 rows]
-constexpr int WA_OFF_BAR = WA_OFF_XCHG + 2 * 2 * 160 * 4;       // mbarriers + tmem slot
-constexpr int WA_SMEM = WA_OFF_BAR + 128 + 128 /*align slack*/;
+constexpr int WA_OFF_M = WA_OFF_BIAS + WA_BIAS_BYTES;         // float [4 slots][2 halves][160 rows]: per-half row maxima
+constexpr int WA_OFF_BAR = WA_OFF_M + 4 * 2 * 160 * 4;        // mbarriers + tmem slot
+constexpr int WA_SMEM = WA_OFF_BAR + 256;
+static_assert(WA_SMEM <= 227 * 1024, "window attention shared-memory budget");
 
-// TMEM columns
-constexpr int WA_TM_S0 = 0, WA_TM_S1 = 160, WA_TM_O0 = 320, WA_TM_O1 = 352, WA_TM_COLS = 512;
+// TMEM columns: S tiles, then per row tile the two partial outputs
+constexpr int WA_TM_S0 = 0, WA_TM_S1 = 160, WA_TM_O = 320, WA_TM_COLS = 512;
+static_assert(WA_TM_O + 4 * WA_ON <= WA_TM_COLS, "TMEM budget");
 
 // UMMA shared-memory descriptor without swizzle: operands live as 8-row x 16-byte "core matrices" (128 contiguous
 // bytes); lbo / sbo are the byte distances between core matrices (K-major: lbo along K, sbo along M/N;
@@ -77,6 +82,11 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -91,24 +101,256 @@ __device__ __forceinline__ uint32_t core_off(int row, int chunk, int cores_per_g
   return static_cast<uint32_t>(((row >> 3) * cores_per_group + chunk) * 128 + (row & 7) * 16);
 }
 
+struct WaShared {
+  uint8_t* smem;
+  uint64_t *qk_full, *qk_empty, *v_full, *v_empty, *s_full, *s_free, *p_full, *o_full;
+  long long* prof;  // profiling hook (lrce_debug_attention_timing): [warp][8] cycle counters of CTA 0, or nullptr
+};
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// mbarrier wait that also accounts the stall to counter `slot` of this warp when the profiling hook is armed. With the
+// hook armed it doubles as a watchdog: a wait longer than ~50 ms records (warp, slot, item) in prof[132..] and raises
+// a CTA-wide abort flag that makes every later wait fall through, so a protocol deadlock ends with a report, not a hang.
+__device__ __forceinline__ void timed_wait(const WaShared& sh, uint64_t* bar, uint32_t parity, int slot, int item = -1) {
+  if (sh.prof == nullptr) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(sh.smem + WA_OFF_BAR + 200);
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*abort_flag) break;
+    if (clock64() - t0 > 100000000LL) {
+      if ((threadIdx.x & 31) == 0) {
+        *abort_flag = 1;
+        sh.prof[132 + (threadIdx.x >> 5)] = (static_cast<long long>(blockIdx.x) << 40) | (static_cast<long long>(slot + 1) << 32) |
+                                            static_cast<unsigned>(item);
+      }
+      break;
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) sh.prof[(threadIdx.x >> 5) * 8 + slot] += clock64() - t0;
+}
+
+// One softmax warp; all twelve run this one function (one copy of the unrolled code in the instruction cache).
+// tile 0: rows 0..127 of every item; tile 1: rows 128..146 of the items whose parity is `parity`, placed in TMEM lanes /
+// A-operand rows lane_base .. lane_base + 31. `half` selects key columns [80 half, 80 half + 80) of the score tile.
+__device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_base, int tile, int half, int lane_base,
+                                          int parity, const bf16* __restrict__ bias_dense, bf16* __restrict__ out,
+                                          const StageGeom& g, int n_items, int nwin, int T, int C, int u_lo, int n_my,
+                                          float scale_log2e, bool shifted) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the pointer must be derived from the __shared__ array itself, otherwise every access below compiles to generic LD/ST
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* sM = reinterpret_cast<float*>(smem + WA_OFF_M);
+  const int prow = lane_base + lane;            // A-operand row of the P tile == TMEM lane
+  const int row = tile ? 128 + lane : prow;     // query row inside the window
+  const int brow = min(row, WA_N - 1);
+  const uint32_t lane_addr = static_cast<uint32_t>(lane_base) << 16;
+  const uint32_t s_addr = tmem_base + lane_addr + (tile ? WA_TM_S1 : WA_TM_S0) + half * WA_HALF;
+  const uint32_t o_addr = tmem_base + lane_addr + WA_TM_O + tile * 2 * WA_ON;  // O_A; O_B at + WA_ON
+  uint8_t* p_row = smem + WA_OFF_P + tile * WA_P_TILE_BYTES + core_off(prow, half * (WA_HALF / 8), WA_KEYS / 8);
+  const bf16* bias_row = reinterpret_cast<const bf16*>(smem + WA_OFF_BIAS) + brow * WA_BIAS_PITCH + half * WA_HALF;
+  const float MASK_L2 = -100.0f * 1.4426950408889634f;
+  // region of this row inside a bottom / right border window (shift 3 on a 7-wide window: the seam is at index 4)
+  const bool rh_i = ((brow / 7) % 7) >= 4, rw_i = (brow % 7) >= 4;
+  const int nw = g.W / g.ww, nh = g.H / g.wh;
+  const int lw = 31 - __clz(nw);  // H/7 and W/7 are powers of two on this path (8, 4, 2, 1)
+  // in-window coordinates of this thread's query row: its token (the output row) is one cyclic wrap per item
+  const int row_d = brow / 49, row_h = (brow / 7) % 7, row_w = brow % 7;
+  // index of this thread among the 384 softmax threads (warps 0-9, 12, 13)
+  const int st = threadIdx.x - (warp < 10 ? 0 : 64);
+
+  float m_prev = 0.f;
+  int tok_prev = 0, seg_prev = 0, head_prev = 0;
+  int head_loaded = -1;
+
+  // epilogue of one item: merge the two half-products and scatter 32 bytes through the inverse remap
+  auto store_o = [&](float m_mine, float m_other, int seg, int tok, int head) {
+    uint32_t oa[16], ob[16];
+    const uint32_t la_u = tmem_ld_32x1(o_addr + 32), lb_u = tmem_ld_32x1(o_addr + WA_ON + 32);
+    tmem_ld_32x16(o_addr + half * 16, oa);
+    tmem_ld_32x16(o_addr + WA_ON + half * 16, ob);
+    tmem_ld_wait();
+    const float la = __uint_as_float(la_u), lb = __uint_as_float(lb_u);
+    const float m_a = half ? m_other : m_mine, m_b = half ? m_mine : m_other;
+    const float m = fmaxf(m_a, m_b);
+    float a = ex2_approx(m_a - m), b = ex2_approx(m_b - m);
+    const float inv = 1.0f / fmaf(a, la, b * lb);
+    a *= inv;
+    b *= inv;
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = fmaf(a, __uint_as_float(oa[i]), b * __uint_as_float(ob[i]));
+    if (row < WA_N) {
+      uint4 o0, o1;
+      o0.x = pack_bf16x2(o[0], o[1]); o0.y = pack_bf16x2(o[2], o[3]); o0.z = pack_bf16x2(o[4], o[5]); o0.w = pack_bf16x2(o[6], o[7]);
+      o1.x = pack_bf16x2(o[8], o[9]); o1.y = pack_bf16x2(o[10], o[11]); o1.z = pack_bf16x2(o[12], o[13]); o1.w = pack_bf16x2(o[14], o[15]);
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(seg) * T + tok) * C + head * 32 + half * 16);
+      dst[0] = o0;
+      dst[1] = o1;
+    }
+  };
+
+  int head = u_lo / n_items, item = u_lo - head * n_items - 1;
+  for (int j = 0; j < n_my; ++j) {
+    if (++item == n_items) { item = 0; ++head; }
+    const int seg = item / nwin, win = item - seg * nwin;
+    if (head != head_loaded) {  // (re)load this head's dense bias; uniform across the 12 softmax warps
+      asm volatile("bar.sync 7, 384;" ::: "memory");
+      const uint4* src = reinterpret_cast<const uint4*>(bias_dense + static_cast<size_t>(head) * WA_N * WA_BIAS_PITCH);
+      uint4* dst = reinterpret_cast<uint4*>(smem + WA_OFF_BIAS);
+      for (int i = st; i < WA_N * WA_BIAS_PITCH / 8; i += 384) dst[i] = __ldg(src + i);
+      asm volatile("bar.sync 7, 384;" ::: "memory");
+      head_loaded = head;
+    }
+    if (tile == 1 && (j & 1) != parity) {
+      // not this warp's item: its only duty is to confirm that its previous O tile has been drained (it has: the
+      // epilogue at the end of the previous iteration) before P v of this item overwrites those TMEM columns
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sh.p_full);
+      // Stay within one phase of the barriers this warp waits on (a parity wait must never lag two phases behind):
+      // o_full(j) cannot be followed by o_full(j+1) before this warp's own arrival on p_full(j+1), and because the tensor
+      // pipe retires S(j+1) before P v(j), its completion also proves that s_full(j+1) — the next barrier this warp
+      // waits on — has completed. (Waiting on s_full(j) here would be wrong: S(j+1) does not depend on this warp and
+      // could complete first, leaving the parity wait two phases behind.)
+      timed_wait(sh, sh.o_full, j & 1, 3, j);
+      continue;
+    }
+    // shift mask of this item: keys are grouped by class (remap.cuh key_slot_377), so it is one additive constant per
+    // 8-column group: -100 for the classes on the far side of the seam of a border window (video_swin_ori.py:357-358)
+    float gm[WA_HALF / 8];
+    {
+      float madd[4] = {0.f, 0.f, 0.f, 0.f};
+      if (shifted) {
+        const bool use_w = ((win % nw) == nw - 1) && g.sw, use_h = (((win / nw) % nh) == nh - 1) && g.sh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool ch = (k >> 1) != 0, cw = (k & 1) != 0;
+          madd[k] = ((use_h && ch != rh_i) || (use_w && cw != rw_i)) ? MASK_L2 : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q8 = 0; q8 < WA_HALF / 8; ++q8) {
+        const int grp = half * (WA_HALF / 8) + q8;
+        gm[q8] = grp < 6 ? madd[0] : (grp < 11 ? madd[1] : (grp < 16 ? madd[2] : madd[3]));
+      }
+    }
+    // the maxima ring is 4 deep: a thread's partner reads slot(j) only in its epilogue of item j, which can run while this
+    // thread is already two items further (never four: P v(j+1) needs the partner's arrival after that epilogue)
+    const int mslot = tile ? ((j >> 1) & 3) : (j & 3);
+    timed_wait(sh, sh.s_full, j & 1, 0, j);
+    tcgen05_fence_after();
+    int tok;
+    {
+      int y = ((win >> lw) & (nh - 1)) * 7 + g.sh + row_h, x = (win & (nw - 1)) * 7 + g.sw + row_w;
+      if (y >= g.H) y -= g.H;
+      if (x >= g.W) x -= g.W;
+      tok = (row_d * g.H + y) * g.W + x;  // == window_source_token_377(g, hW, wW, brow)
+    }
+    // ---- pass 1: t = s * scale * log2e + bias (+ mask), maximum of this thread's 80 columns; t stays in registers.
+    // Pad columns carry a bias of -inf (lrce_window_bias_pack), so they need no special case.
+    float t[WA_HALF];
+    float mx = -INFINITY;
+    {
+      // all five TMEM loads are in flight together (one exposed latency); the raw scores land in t's own registers
+      uint32_t* raw = reinterpret_cast<uint32_t*>(t);
+#pragma unroll
+      for (int c = 0; c < WA_HALF; c += 16) tmem_ld_32x16(s_addr + c, raw + c);
+      tmem_ld_wait();
+    }
+    // S(j) now lives in registers: release the accumulator at once, so that S(j+1) is computed under this item's softmax
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sh.s_free);
+#pragma unroll
+    for (int c = 0; c < WA_HALF; c += 8) {
+      const uint4 b4 = *reinterpret_cast<const uint4*>(bias_row + c);
+      const float2 b01 = unpack_bf16x2(b4.x), b23 = unpack_bf16x2(b4.y), b45 = unpack_bf16x2(b4.z), b67 = unpack_bf16x2(b4.w);
+      const float bb[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
+      const float ma = gm[c / 8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = fmaf(t[c + e], scale_log2e, bb[e]) + ma;
+        t[c + e] = v;
+        mx = fmaxf(mx, v);
+      }
+    }
+    sM[(mslot * 2 + half) * 160 + row] = mx;  // published before this warp's arrival on p_full(j)
+    // P v of the previous item must have finished reading the P tile before it is refilled
+    if (tile == 0 && j > 0) timed_wait(sh, sh.o_full, (j - 1) & 1, 1, j);
+    // ---- pass 2: p = exp2(t - max) -> bf16 A-operand tile
+#pragma unroll
+    for (int c = 0; c < WA_HALF; c += 8) {
+      float p[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) p[e] = ex2_approx(t[c + e] - mx);
+      uint4 u;
+      u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
+      u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+      *reinterpret_cast<uint4*>(p_row + (c / 8) * 128) = u;
+    }
+    // ---- epilogue of the previous item of the main tile: must drain O before P v of THIS item overwrites it
+    if (tile == 0 && j > 0) {
+      // the partner published its maximum of item j-1 before arriving on p_full(j-1), and o_full(j-1) (waited above)
+      // completed after that
+      tcgen05_fence_after();
+      store_o(m_prev, sM[((((j - 1) & 3)) * 2 + (half ^ 1)) * 160 + row], seg_prev, tok_prev, head_prev);
+      tcgen05_fence_before();
+    }
+    fence_proxy_async_smem();  // P writes -> visible to the tensor core
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sh.p_full);
+    if (tile == 0) {
+      m_prev = mx; tok_prev = tok; seg_prev = seg; head_prev = head;
+    } else {
+      // leftover rows: finish this item right away (this warp idles during the next item anyway)
+      timed_wait(sh, sh.o_full, j & 1, 4, j);
+      tcgen05_fence_after();
+      store_o(mx, sM[(mslot * 2 + (half ^ 1)) * 160 + row], seg, tok, head);
+      tcgen05_fence_before();
+    }
+  }
+  if (tile == 0 && n_my > 0) {
+    timed_wait(sh, sh.o_full, (n_my - 1) & 1, 5, n_my);
+    tcgen05_fence_after();
+    store_o(m_prev, sM[(((n_my - 1) & 3) * 2 + (half ^ 1)) * 160 + row], seg_prev, tok_prev, head_prev);
+    tcgen05_fence_before();
+  }
+}
+
+// registers are granted per group of four warps, so 14 warps get the same 128 registers per thread as 16 would
 __global__ void __launch_bounds__(WA_THREADS, 1)
 window_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const bf16* __restrict__ bias_dense,
-                        StageGeom g, int n_seg, int C, int n_heads, float scale_log2e) {
+                        StageGeom g, int n_seg, int C, int n_heads, float scale_log2e, long long* prof) {
   // NOTE: pointers must stay derived from the __shared__ array itself (no integer round trip), otherwise the compiler
   // falls back to generic LD/ST for every shared-memory access
   extern __shared__ __align__(128) uint8_t smem[];
-  const bf16* sBias = reinterpret_cast<const bf16*>(smem + WA_OFF_BIAS);
-  int* sTok = reinterpret_cast<int*>(smem + WA_OFF_TOK);
-  uint8_t* sRid = smem + WA_OFF_RID;
-  float* sX = reinterpret_cast<float*>(smem + WA_OFF_XCHG);
-  uint64_t* bar_qk_full = reinterpret_cast<uint64_t*>(smem + WA_OFF_BAR);  // [2]
-  uint64_t* bar_qk_empty = bar_qk_full + 2;                                // [2]
-  uint64_t* bar_v_full = bar_qk_empty + 2;                                 // [2]
-  uint64_t* bar_v_empty = bar_v_full + 2;                                  // [2]
-  uint64_t* bar_s_full = bar_v_empty + 2;
-  uint64_t* bar_p_full = bar_s_full + 1;
-  uint64_t* bar_o_full = bar_p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_full + 1);
+  WaShared sh;
+  sh.smem = smem;
+  sh.prof = prof;
+  sh.qk_full = reinterpret_cast<uint64_t*>(smem + WA_OFF_BAR);  // [2]
+  sh.qk_empty = sh.qk_full + 2;                                 // [2]
+  sh.v_full = sh.qk_empty + 2;                                  // [2]
+  sh.v_empty = sh.v_full + 2;                                   // [2]
+  sh.s_full = sh.v_empty + 2;
+  sh.s_free = sh.s_full + 1;
+  sh.p_full = sh.s_free + 1;
+  sh.o_full = sh.p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sh.o_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwin = windows_per_segment(g);
@@ -121,234 +363,160 @@ window_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, co
   const int u_lo = static_cast<int>(n_units * blockIdx.x / gridDim.x);
   const int u_hi = static_cast<int>(n_units * (blockIdx.x + 1) / gridDim.x);
   const int n_my = u_hi - u_lo;
+  if (prof != nullptr && blockIdx.x == 0 && tid == 0) prof[16 * 8 + 2] = clock64();
 
-  // ---- one-time setup: zero the q/k/v staging (pad rows stay zero forever), load this head's bias, barriers, TMEM
+  // ---- one-time setup: zero the q/k/v staging (pad rows stay zero forever), the ones column of v, barriers, TMEM
   for (int i = tid; i < 2 * WA_QKV_BYTES / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem + WA_OFF_QKV)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 2 * WA_P_TILE_BYTES / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem + WA_OFF_P)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = tid; i < 2 * WA_KEYS; i += WA_THREADS) {
+    const int buf = i / WA_KEYS, r = i - buf * WA_KEYS;
+    *reinterpret_cast<uint4*>(smem + WA_OFF_QKV + buf * WA_QKV_BYTES + WA_Q_BYTES + WA_K_BYTES + core_off(r, 4, WA_VCH)) =
+        make_uint4(0x00003F80u, 0, 0, 0);  // bf16 1.0 in dim 32, zeros in 33..39
+  }
   if (warp == 11 && lane == 0) {
+    *reinterpret_cast<volatile int*>(smem + WA_OFF_BAR + 200) = 0;  // watchdog abort flag (profiling hook only)
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_qk_full[b], 2);  // the q loader and the k loader
-      mbar_init(&bar_qk_empty[b], 1);
-      mbar_init(&bar_v_full[b], 1);
-      mbar_init(&bar_v_empty[b], 1);
+      mbar_init(&sh.qk_full[b], 1);
+      mbar_init(&sh.qk_empty[b], 1);
+      mbar_init(&sh.v_full[b], 1);
+      mbar_init(&sh.v_empty[b], 1);
     }
-    mbar_init(bar_s_full, 1);
-    mbar_init(bar_p_full, 10);
-    mbar_init(bar_o_full, 1);
+    mbar_init(sh.s_full, 1);
+    mbar_init(sh.s_free, 10);  // 8 main warps + the 2 leftover warps of the item
+    mbar_init(sh.p_full, WA_SOFTMAX_ARRIVALS);
+    mbar_init(sh.o_full, 1);
     fence_barrier_init();
   }
   if (warp == 10) tmem_alloc(tmem_slot, WA_TM_COLS);
-  fence_proxy_async_smem();  // the zero fill above must be visible to the tensor core's operand reads
+  fence_proxy_async_smem();  // the fills above must be visible to the tensor core's operand reads
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9 || warp == 10 || warp == 13) {
-    // ===================================================================== loaders: warp 9 -> q, 10 -> k, 13 -> v
-    const int part = (warp == 9) ? 0 : (warp == 10 ? 1 : 2);
-    int* myTok = sTok + part * WA_RING * 160;
-    uint64_t* full = (part == 2) ? bar_v_full : bar_qk_full;
-    uint64_t* empty = (part == 2) ? bar_v_empty : bar_qk_empty;
-    const uint32_t part_off = (part == 0) ? 0u : (part == 1 ? static_cast<uint32_t>(WA_Q_BYTES) : static_cast<uint32_t>(WA_Q_BYTES + WA_K_BYTES));
+  if (warp == 10) {
+    // ===================================================================== loader (q, k, v)
     const int sub = lane >> 2, ch = lane & 3;  // 4 lanes fetch the 64 contiguous bytes of one row
+    // A lane always serves the same window rows r = sub + 8k: their in-window coordinates and staging offsets are fixed
+    // for the whole kernel, so the per-item work is the cyclic wrap of 19 (y, x) pairs and 3 x 19 cp.async.
+    constexpr int NK = (WA_N + 7) / 8;  // 19
+    uint32_t r_hw[NK], r_dq[NK], r_dk[NK], r_dv[NK];
+    int r_tok0[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int r = min(sub + 8 * k, WA_N - 1);
+      const int d = r / 49, rem = r - d * 49, h = rem / 7, w = rem - h * 7;
+      r_hw[k] = static_cast<uint32_t>(h << 8 | w);
+      r_tok0[k] = d * g.H * g.W;
+      // q rows 128..146 go to row tile 1 (lane quarter 0; + 32 rows for odd items, added per item); k / v rows go to their
+      // class-grouped slot (remap.cuh key_slot_377)
+      const int slot = key_slot_377(r);
+      r_dq[k] = core_off(r, ch, 4);
+      r_dk[k] = WA_Q_BYTES + core_off(slot, ch, 4);
+      r_dv[k] = WA_Q_BYTES + WA_K_BYTES + core_off(slot, ch, WA_VCH);
+    }
+    const int lw = 31 - __clz(g.W / 7);  // H/7 and W/7 are powers of two on this path (8, 4, 2, 1)
+    const int nh_mask = g.H / 7 - 1, nw_mask = g.W / 7 - 1;
+    int head = u_lo / n_items, item = u_lo - head * n_items;
     for (int j = 0; j < n_my; ++j) {
-      const int buf = j & 1, slot = j & (WA_RING - 1);
-      const int unit = u_lo + j;
-      const int head = unit / n_items, item = unit - head * n_items;
+      const int buf = j & 1;
       const int seg = item / nwin, win = item - seg * nwin;
-      mbar_wait(&empty[buf], ((j >> 1) & 1) ^ 1);
-      for (int r = lane; r < WA_N; r += 32) {
-        myTok[slot * 160 + r] = window_source_token(g, win, r);
-        if (part == 0) sRid[slot * 160 + r] = static_cast<uint8_t>(shifted ? shift_region_id(g, win, r) : 0);
+      const int ybase = ((win >> lw) & nh_mask) * 7 + g.sh, xbase = (win & nw_mask) * 7 + g.sw;
+      const bf16* base = qkv + static_cast<size_t>(seg) * T * 3 * C + head * 32 + ch * 8;
+      const uint32_t sbuf = smem_u32(smem + WA_OFF_QKV + buf * WA_QKV_BYTES);
+      const uint32_t left_off = buf ? 32 * 64 : 0;  // odd items: 32 rows further down (TMEM lane quarter 1)
+      int tok[NK];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        int y = ybase + static_cast<int>(r_hw[k] >> 8), x = xbase + static_cast<int>(r_hw[k] & 0xff);
+        if (y >= g.H) y -= g.H;
+        if (x >= g.W) x -= g.W;
+        tok[k] = (r_tok0[k] + y * g.W + x) * 3 * C;
       }
-      __syncwarp();
-      const bf16* base = qkv + static_cast<size_t>(seg) * T * 3 * C + part * C + head * 32 + ch * 8;
-      const uint32_t sbuf = smem_u32(smem + WA_OFF_QKV + buf * WA_QKV_BYTES) + part_off;
-#pragma unroll 4
-      for (int r = sub; r < WA_N; r += 8)
-        cp_async_16(sbuf + core_off(r, ch, 4), base + static_cast<size_t>(myTok[slot * 160 + r]) * 3 * C);
-      asm volatile("cp.async.wait_all;" ::: "memory");
+      timed_wait(sh, &sh.qk_empty[buf], ((j >> 1) & 1) ^ 1, 0, j);
+      const long long tl0 = clock64();
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        if (sub + 8 * k < WA_N) cp_async_16(sbuf + r_dq[k] + (k >= 16 ? left_off : 0u), base + tok[k]);
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        if (sub + 8 * k < WA_N) cp_async_16(sbuf + r_dk[k], base + C + tok[k]);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      timed_wait(sh, &sh.v_empty[buf], ((j >> 1) & 1) ^ 1, 3, j);
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        if (sub + 8 * k < WA_N) cp_async_16(sbuf + r_dv[k], base + 2 * C + tok[k]);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const long long tl1 = clock64();
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[buf]);
+      if (lane == 0) mbar_arrive(&sh.qk_full[buf]);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.v_full[buf]);
+      if (sh.prof != nullptr && lane == 0 && blockIdx.x == 0) {
+        sh.prof[warp * 8 + 1] += tl1 - tl0;        // cp.async issue (incl. the wait for the v buffer)
+        sh.prof[warp * 8 + 2] += clock64() - tl1;  // waiting for the data
+      }
+      if (++item == n_items) { item = 0; ++head; }
     }
   } else if (warp == 11) {
     // ===================================================================== MMA issuer
     if (lane == 0 && n_my > 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_KEYS);               // A, B K-major
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);       // B (= v) MN-major
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_KEYS);            // A, B K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, WA_ON) | (1u << 16);  // B (= v) MN-major
+      // Descriptors of one operand differ only in their start-address field (bits 0..13, in 16-byte units), so every
+      // further MMA of a sequence costs one 64-bit add instead of a fresh encode.
+      const uint32_t smem0 = smem_u32(smem);
       auto issue_s = [&](int j) {
-        const uint32_t b = smem_u32(smem + WA_OFF_QKV + (j & 1) * WA_QKV_BYTES);
-        const uint32_t q_addr = b, k_addr = b + WA_Q_BYTES;
+        const uint32_t b = smem0 + WA_OFF_QKV + (j & 1) * WA_QKV_BYTES;
+        const uint64_t dq = umma_desc_nosw(b, 128, 512), dk = umma_desc_nosw(b + WA_Q_BYTES, 128, 512);
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk)
-            umma_bf16_ss(tmem_base + (tile ? WA_TM_S1 : WA_TM_S0),
-                         umma_desc_nosw(q_addr + tile * (16 * 512) + kk * 256, 128, 512),
-                         umma_desc_nosw(k_addr + kk * 256, 128, 512), idesc_s, kk);
-        umma_commit(bar_s_full);
+            umma_bf16_ss(tmem_base + (tile ? WA_TM_S1 : WA_TM_S0), dq + ((tile * (16 * 512) + kk * 256) >> 4), dk + ((kk * 256) >> 4),
+                         idesc_s, kk);
+        umma_commit(sh.s_full);
+        umma_commit(&sh.qk_empty[j & 1]);
       };
-      mbar_wait(&bar_qk_full[0], 0);
+      mbar_wait(&sh.qk_full[0], 0);
       tcgen05_fence_after();
       issue_s(0);
-      umma_commit(&bar_qk_empty[0]);
       for (int j = 0; j < n_my; ++j) {
-        mbar_wait(bar_p_full, j & 1);  // softmax(j) done: S buffer free, P(j) in smem, O(j-1) drained
-        tcgen05_fence_after();
         if (j + 1 < n_my) {
-          mbar_wait(&bar_qk_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          timed_wait(sh, sh.s_free, j & 1, 0, j);  // every softmax warp holds S(j) in registers
+          timed_wait(sh, &sh.qk_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 1, j);
           tcgen05_fence_after();
           issue_s(j + 1);
-          umma_commit(&bar_qk_empty[(j + 1) & 1]);
         }
-        mbar_wait(&bar_v_full[j & 1], (j >> 1) & 1);
+        timed_wait(sh, sh.p_full, j & 1, 2, j);  // P(j) in smem, O(j-1) drained
+        timed_wait(sh, &sh.v_full[j & 1], (j >> 1) & 1, 3, j);
         tcgen05_fence_after();
-        const uint32_t v_addr = smem_u32(smem + WA_OFF_QKV + (j & 1) * WA_QKV_BYTES) + WA_Q_BYTES + WA_K_BYTES;
-        const uint32_t p_addr = smem_u32(smem + WA_OFF_P);
+        const uint64_t dv = umma_desc_nosw(smem0 + WA_OFF_QKV + (j & 1) * WA_QKV_BYTES + WA_Q_BYTES + WA_K_BYTES,
+                                           /*lbo: key groups*/ WA_VCH * 128, /*sbo: dim groups*/ 128);
+        const uint64_t dp = umma_desc_nosw(smem0 + WA_OFF_P, 128, (WA_KEYS / 8) * 128);
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
           for (int kk = 0; kk < WA_KEYS / 16; ++kk)
-            umma_bf16_ss(tmem_base + (tile ? WA_TM_O1 : WA_TM_O0),
-                         umma_desc_nosw(p_addr + tile * WA_P_TILE_BYTES + kk * 256, 128, (WA_KEYS / 8) * 128),
-                         umma_desc_nosw(v_addr + kk * 1024, /*lbo: key groups*/ 512, /*sbo: dim groups*/ 128), idesc_o, kk);
-        umma_commit(bar_o_full);
-        umma_commit(&bar_v_empty[j & 1]);
+            umma_bf16_ss(tmem_base + WA_TM_O + (tile * 2 + (kk >= WA_HALF / 16 ? 1 : 0)) * WA_ON,
+                         dp + ((tile * WA_P_TILE_BYTES + kk * 256) >> 4), dv + ((kk * (2 * WA_VCH * 128)) >> 4), idesc_o,
+                         (kk % (WA_HALF / 16)) != 0);
+        umma_commit(sh.o_full);
+        umma_commit(&sh.v_empty[j & 1]);
       }
     }
   } else {
-    // ===================================================================== softmax + epilogue (warps 0-8, 12)
-    const int tile = (warp >= 8) ? 1 : 0;
-    const int q = warp & 3;                              // TMEM lane quarter
-    const int half = (warp >= 8) ? (warp == 12) : (warp >> 2);
-    const int row = tile * 128 + q * 32 + lane;          // query row inside the window
-    const int brow = min(row, WA_N - 1);
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int pair_bar = 1 + tile * 4 + q;               // named barrier shared with the warp owning the other columns
-    const float MASK_L2 = -100.0f * 1.4426950408889634f;
-    const int col0 = half * 80;
-    float inv_prev = 0.f;
-    int tok_prev = 0, seg_prev = 0, head_prev = 0, head_loaded = -1;
-    const int st = (warp < 9) ? tid : (tid - 96);  // index among the 320 softmax threads (warps 0-8 and 12)
-
-    auto store_o = [&](float inv, int seg, int tok, int head, bool valid) {
-      uint32_t acc[16];
-      tmem_ld_32x16(tmem_base + lane_addr + (tile ? WA_TM_O1 : WA_TM_O0) + half * 16, acc);
-      tmem_ld_wait();
-      if (valid) {
-        uint4 o0, o1;
-        o0.x = pack_bf16x2(__uint_as_float(acc[0]) * inv, __uint_as_float(acc[1]) * inv);
-        o0.y = pack_bf16x2(__uint_as_float(acc[2]) * inv, __uint_as_float(acc[3]) * inv);
-        o0.z = pack_bf16x2(__uint_as_float(acc[4]) * inv, __uint_as_float(acc[5]) * inv);
-        o0.w = pack_bf16x2(__uint_as_float(acc[6]) * inv, __uint_as_float(acc[7]) * inv);
-        o1.x = pack_bf16x2(__uint_as_float(acc[8]) * inv, __uint_as_float(acc[9]) * inv);
-        o1.y = pack_bf16x2(__uint_as_float(acc[10]) * inv, __uint_as_float(acc[11]) * inv);
-        o1.z = pack_bf16x2(__uint_as_float(acc[12]) * inv, __uint_as_float(acc[13]) * inv);
-        o1.w = pack_bf16x2(__uint_as_float(acc[14]) * inv, __uint_as_float(acc[15]) * inv);
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(seg) * T + tok) * C + head * 32 + half * 16);
-        dst[0] = o0;
-        dst[1] = o1;
-      }
-    };
-
-    for (int j = 0; j < n_my; ++j) {
-      const int slot = j & (WA_RING - 1);
-      const int unit = u_lo + j;
-      const int head = unit / n_items, item = unit - head * n_items;
-      const int seg = item / nwin, win = item - seg * nwin;
-      if (head != head_loaded) {  // (re)load this head's dense bias; uniform across the softmax warps
-        asm volatile("bar.sync 7, 320;" ::: "memory");
-        const uint4* src = reinterpret_cast<const uint4*>(bias_dense + static_cast<size_t>(head) * WA_N * WA_BIAS_PITCH);
-        uint4* dst = reinterpret_cast<uint4*>(smem + WA_OFF_BIAS);
-        for (int i = st; i < WA_N * WA_BIAS_PITCH / 8; i += 320) dst[i] = __ldg(src + i);
-        asm volatile("bar.sync 7, 320;" ::: "memory");
-        head_loaded = head;
-      }
-      bool need_mask = false;
-      if (shifted) {
-        const int nw = g.W / g.ww, nh = g.H / g.wh;
-        need_mask = ((win % nw) == nw - 1 && g.sw) || (((win / nw) % nh) == nh - 1 && g.sh);
-      }
-      mbar_wait(bar_s_full, j & 1);
-      tcgen05_fence_after();
-      const int tok = sTok[slot * 160 + brow];
-      const int rid = sRid[slot * 160 + brow];
-      // ---- pass 1: t = s * scale * log2e + bias (+ mask), running max; 80 columns per thread kept in registers
-      float t[80];
-      float mx = -INFINITY;
-      const uint32_t s_addr = tmem_base + lane_addr + (tile ? WA_TM_S1 : WA_TM_S0) + col0;
-#pragma unroll
-      for (int c = 0; c < 80; c += 16) {
-        uint32_t acc[16];
-        tmem_ld_32x16(s_addr + c, acc);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; i += 8) {
-          const int col = col0 + c + i;  // 8 consecutive key columns
-          if (col < WA_BIAS_PITCH) {     // compile-time after unrolling except for `half`
-            const uint4 b4 = *reinterpret_cast<const uint4*>(sBias + brow * WA_BIAS_PITCH + col);
-            const float2 b01 = unpack_bf16x2(b4.x), b23 = unpack_bf16x2(b4.y), b45 = unpack_bf16x2(b4.z), b67 = unpack_bf16x2(b4.w);
-            const float bb[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float v = fmaf(__uint_as_float(acc[i + e]), scale_log2e, bb[e]);
-              if (need_mask && sRid[slot * 160 + min(col + e, WA_N - 1)] != rid) v += MASK_L2;
-              if (col + e >= WA_N) v = -INFINITY;
-              t[c + i + e] = v;
-              mx = fmaxf(mx, v);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) t[c + i + e] = -INFINITY;
-          }
-        }
-      }
-      tcgen05_fence_before();  // all TMEM reads of S(j) are complete (wait::ld above)
-      sX[(0 * 2 + half) * 160 + row] = mx;  // rows of tile 1 are stored at 32 + (row - 128)
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      mx = fmaxf(mx, sX[(0 * 2 + (half ^ 1)) * 160 + row]);
-      // ---- epilogue of the previous item (its P v finished long ago); also frees the P buffer for this item
-      if (j > 0) {
-        mbar_wait(bar_o_full, (j - 1) & 1);
-        tcgen05_fence_after();
-        store_o(inv_prev, seg_prev, tok_prev, head_prev, row < WA_N);
-        tcgen05_fence_before();
-      }
-      // ---- pass 2: p = exp2(t - max) -> bf16 A-operand tile, row sum
-      float sum = 0.f;
-      uint8_t* p_row = smem + WA_OFF_P + tile * WA_P_TILE_BYTES;
-#pragma unroll
-      for (int c = 0; c < 80; c += 8) {
-        float p[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          p[e] = ex2_approx(t[c + e] - mx);
-          sum += p[e];
-        }
-        uint4 u;
-        u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-        u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-        *reinterpret_cast<uint4*>(p_row + core_off(q * 32 + lane, (col0 + c) >> 3, WA_KEYS / 8)) = u;
-      }
-      sX[(1 * 2 + half) * 160 + row] = sum;
-      fence_proxy_async_smem();  // P writes -> visible to the tensor core
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      sum += sX[(1 * 2 + (half ^ 1)) * 160 + row];
-      inv_prev = 1.0f / sum;
-      tok_prev = tok;
-      seg_prev = seg;
-      head_prev = head;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full);
-    }
-    if (n_my > 0) {
-      mbar_wait(bar_o_full, (n_my - 1) & 1);
-      tcgen05_fence_after();
-      store_o(inv_prev, seg_prev, tok_prev, head_prev, row < WA_N);
-      tcgen05_fence_before();
-    }
+    // ===================================================================== softmax + epilogue (12 warps)
+    const int tile = warp >= 8;
+    const int half = tile ? (warp >= 12) : (warp >> 2);
+    const int parity = warp & 1;  // warps 8, 12: even items (TMEM lanes 0..31); 9, 13: odd items (lanes 32..63)
+    softmax_warp(sh, tmem_base, tile, half, tile ? parity * 32 : (warp & 3) * 32, parity, bias_dense, out, g, n_items, nwin, T,
+                 C, u_lo, n_my, scale_log2e, shifted);
   }
 
   tcgen05_fence_before();
@@ -357,32 +525,50 @@ window_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, co
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, WA_TM_COLS);
   }
+  if (prof != nullptr && blockIdx.x == 0 && tid == 0) {
+    prof[16 * 8] = n_my;
+    prof[16 * 8 + 1] = clock64() - prof[16 * 8 + 2];
+  }
 }
 
-// bias_dense[h][i][j] = table[rel_index(i, j)][h] * log2(e), j padded to 152 with zeros
+// bias_dense[h][i][key_slot(j)] = table[rel_index(i, j)][h] * log2(e); the 13 pad columns of the score tile hold -inf
 __global__ void build_dense_bias_kernel(const float* __restrict__ table, bf16* __restrict__ dense, StageGeom g,
                                         int n_heads) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = n_heads * WA_N * WA_BIAS_PITCH;
   if (idx >= total) return;
   const int j = idx % WA_BIAS_PITCH, i = (idx / WA_BIAS_PITCH) % WA_N, h = idx / (WA_BIAS_PITCH * WA_N);
-  float v = 0.f;
   if (j < WA_N) {
     const int rel = rel_pos_offset(g, i) - rel_pos_offset(g, j) + REL_POS_CENTER;
-    v = table[static_cast<size_t>(rel) * n_heads + h] * 1.4426950408889634f;
+    dense[idx - j + key_slot_377(j)] = __float2bfloat16(table[static_cast<size_t>(rel) * n_heads + h] * 1.4426950408889634f);
+  } else {
+    // thread j = 147 + p fills the p-th pad column: 4 after class 1, 4 after class 2, 5 after class 3
+    const int p = j - WA_N;
+    const int col = p < 4 ? 84 + p : (p < 8 ? 124 + (p - 4) : 155 + (p - 8));
+    dense[idx - j + col] = __float2bfloat16(-INFINITY);
   }
-  dense[idx] = __float2bfloat16(v);
 }
 
 }  // namespace lrce
 
 using namespace lrce;
 
+static long long* g_attn_prof = nullptr;
+// Profiling hook, not part of the product path: when buf (device, 16*8+3 zeroed int64) is non-NULL, CTA 0 of the following
+// lrce_window_attention_bf16 launches (buf: 16*8+3+1+16 zeroed int64) accumulates, per warp, the cycles spent in each kind of mbarrier wait
+// (softmax warps: [0] S ready, [1] P v done, [2] foreign-item waits; loaders: [0] buffer free, [1] issue, [2] data landed;
+// MMA: [0] S released, [1] q/k landed, [2] P ready, [3] v landed) plus [128] items and [129] total cycles of CTA 0.
+extern "C" int lrce_debug_attention_timing(long long* buf) {
+  g_attn_prof = buf;
+  return LRCE_OK;
+}
+
 static int geom_3x7x7(StageGeom* g, int D, int H, int W, int sh, int sw) {
   LRCE_REQUIRE(D == 3 && H % 7 == 0 && W % 7 == 0 && H > 0 && W > 0,
                "window attention is specialised for the clamped (3,7,7) window of LRCE's 5-frame segments; got grid "
                "(%d,%d,%d)", D, H, W);
-  LRCE_REQUIRE(sh >= 0 && sh < 7 && sw >= 0 && sw < 7, "shift must be in [0,7)");
+  LRCE_REQUIRE((sh == 0 || sh == 3) && (sw == 0 || sw == 3),
+               "window attention is specialised for Swin's shift = window // 2 = 3 (or 0); got (%d,%d)", sh, sw);
   g->D = D; g->H = H; g->W = W; g->wd = 3; g->wh = 7; g->ww = 7; g->sd = 0; g->sh = sh; g->sw = sw;
   return LRCE_OK;
 }
@@ -411,7 +597,7 @@ extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
   window_attention_kernel<<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g,
-      n_seg, C, n_heads, scale_log2e);
+      n_seg, C, n_heads, scale_log2e, g_attn_prof);
   return check_launch("window_attention_kernel");
 }
 

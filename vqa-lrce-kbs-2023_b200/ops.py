@@ -7,7 +7,7 @@ from . import _lib
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_LN = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 WINDOW = (3, 7, 7)  # effective Swin window on LRCE's 5-frame segments
-BIAS_PITCH = 152
+BIAS_PITCH = 160
 
 # count of kernels launched through this module (bench.py reports it as gpu_launches)
 launches = 0
@@ -148,7 +148,8 @@ def remap_index(dims, window, shift, device="cuda"):
 
 
 def window_bias_pack(table):
-    """relative_position_bias_table fp32 [2535, nH] -> dense bf16 [nH, 147, 152] (pre-multiplied by log2 e)."""
+    """relative_position_bias_table fp32 [2535, nH] -> dense bf16 [nH, 147, 160] (pre-multiplied by log2 e; columns in the
+    kernel's class-grouped key order, pad columns -inf)."""
     _req(table, torch.float32, "table")
     assert table.is_contiguous() and table.shape[0] == 2535
     nh = table.shape[1]

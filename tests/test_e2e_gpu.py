@@ -80,3 +80,29 @@ def test_msvd_b32_batch_invariance(golden, msvd):
     assert (y - ref[None]).abs().max().item() < 0.25
     assert torch.equal(y.argmax(-1), ref.argmax(-1)[None].expand(16, 2))
     assert (y - y[:1]).abs().max().item() < 1e-3  # same kernels, same data -> same answer wherever the clip sits
+
+
+def test_training_step_matches_inference_path_and_has_grads():
+    """BASELINE config 5 (tgif-frameqa training step): with dropout off, the differentiable encoder path must reproduce
+    the kernel path's logits (same algorithm, bf16 both), and backward must reach every encoder parameter and nothing
+    else."""
+    import lrce_b200
+
+    m = lrce_b200.E2EOpenEnded(num_classes=1000, text_seq_len=30, drop_out_rate=0.0, pretrained=False, **CFG)
+    m.load_state_dict(W.make_e2e_state_dict(1000, 30, 3, seed=0), strict=True)
+    m = m.cuda().train()
+    m.text_extractor.eval()  # HF BERT's own dropout would decorrelate the two passes being compared
+    clips, ids, mask, types = W.make_inputs(2, 3, 30, seed=1)
+    args = (clips.cuda(), ids.cuda(), mask.cuda(), types.cuda())
+    with torch.no_grad():
+        y_kernel = m(*args)
+    y = m(*args)
+    assert y.requires_grad and y.shape == y_kernel.shape
+    assert (y - y_kernel).abs().max().item() < 0.25, (y - y_kernel).abs().max().item()
+    loss = torch.nn.functional.cross_entropy(y, torch.tensor([3, 7], device="cuda"))
+    loss.backward()
+    enc = list(m.fusion_model.parameters())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in enc)
+    assert sum(p.grad.abs().sum().item() for p in enc) > 0
+    assert all(p.grad is None for p in m.video_extractor.parameters())
+    assert all(p.grad is None for p in m.text_extractor.parameters())

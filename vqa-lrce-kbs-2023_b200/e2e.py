@@ -43,9 +43,12 @@ class E2EBase(nn.Module):
         cur = torch.cuda.current_stream()
         side = self._side_stream(video_clips.device)
         side.wait_stream(cur)
-        video_features = self.extract_video_features(video_clips)
-        with torch.cuda.stream(side):
-            texts_features = self.extract_text_features(texts, texts_attention_mask, texts_type_ids)
+        # The extractors are forward-only kernels: in a training step (grad enabled) they run without autograd and only
+        # the cross-modal encoder is differentiated — the trainable part BASELINE.json's config 5 names.
+        with torch.no_grad():
+            video_features = self.extract_video_features(video_clips)
+            with torch.cuda.stream(side):
+                texts_features = self.extract_text_features(texts, texts_attention_mask, texts_type_ids)
         cur.wait_stream(side)
         texts_features.record_stream(cur)
         return self.fusion_model(video_features, texts_features, texts_attention_mask)

@@ -185,10 +185,46 @@ class LRCEOpenEnded(nn.Module):
             self._states[key] = st
         return st
 
+    # -------------------------------------------------------------------------------------------------------------
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _encode_autograd(self, video_features, text_features, n_cand, act=ops.ACT_NONE):
+        """Training step of the encoder (BASELINE.json config 5): the same algorithm expressed on the module's own
+        parameters with differentiable PyTorch library ops under bf16 autocast, so that autograd provides the backward
+        pass (hand-written backward kernels are not built yet — DESIGN.md §7). Dropout is active in train() mode, as in
+        the reference (fusionv3.py:190-191, :49). The extractors feeding it stay on liblrce_b200 and are not
+        differentiated through. video_features (B, S, T, P, Dv); text_features (B*n_cand, L, 768)."""
+        ve, te, ft = self.video_pos_embed, self.question_pos_embed, self.fusion_transformer
+        B, S, T, P, _ = video_features.shape
+        Bq = text_features.shape[0]
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            v = video_features.float()
+            if hasattr(self, "projection_layer"):
+                v = self.projection_layer(v)  # fusionv3.py:184-185
+            # VideoPosEmbed (embedding.py:47-63): CLS per frame, position / frame-index / segment embeddings, LayerNorm
+            v = torch.cat([ve.emb_cls.expand(B, S, T, -1, -1), v], dim=3)
+            v = ve.layer_norm(v + ve.emb_pos + ve.emb_len + ve.emb_clip).view(B, S, T * (P + 1), -1)
+            # TextPosEmbed (embedding.py:17-23)
+            t = torch.cat([te.emb_cls.expand(Bq, -1, -1), text_features.float()], dim=1)
+            t = te.layer_norm(t + te.emb_pos)
+            v, t = self.video_dropout(v), self.question_dropout(t)
+            if n_cand > 1:  # fusionv3.py:259: every candidate attends the same clip
+                v = v.unsqueeze(1).expand(-1, n_cand, -1, -1, -1).flatten(0, 1)
+            tok = ft.summarization_token.expand(Bq, -1, -1)
+            for s in range(S):  # fusionv3.py:41-49
+                mem = torch.cat([v[:, s], t], dim=1)
+                tok = ft.dropout(ft.fusion_layer_norm(tok + ft.transformer(tok, mem)))
+            out = self.final_fc(tok.squeeze(1))
+        out = out.float()
+        return torch.relu(out) if act == ops.ACT_RELU else out
+
     def forward(self, video_features, text_features, texts_attention_mask=None, taps=None):
         """(B, S, T, 49, Dv), (B, L, 768) -> (B, num_classes) fp32 (fusionv3.py:168-198). `texts_attention_mask` is
         accepted and ignored, exactly like the reference (fusionv3.py:31)."""
         B = video_features.shape[0]
+        if self._wants_grad() and taps is None:
+            return self._encode_autograd(video_features, text_features, 1).view(B, -1)
         return self._encode(video_features, text_features, 1, taps=taps).view(B, -1)
 
 
@@ -203,6 +239,8 @@ class LRCEMultipleChoice(LRCEOpenEnded):
     def forward(self, video_features, text_features, texts_attention_mask=None, taps=None):
         """text_features (B, n_cand, L, 768) -> (B, n_cand) (fusionv3.py:230-265)"""
         B, n_cand = text_features.shape[:2]
+        if self._wants_grad() and taps is None:
+            return self._encode_autograd(video_features, text_features.flatten(0, 1), n_cand).view(B, n_cand)
         return self._encode(video_features, text_features.flatten(0, 1), n_cand, taps=taps).view(B, n_cand)
 
 
@@ -217,4 +255,6 @@ class LRCECount(LRCEOpenEnded):
     def forward(self, video_features, text_features, texts_attention_mask=None, taps=None):
         """(B,) = relu(final_fc(token)) (fusionv3.py:360-369)"""
         B = video_features.shape[0]
+        if self._wants_grad() and taps is None:
+            return self._encode_autograd(video_features, text_features, 1, act=ops.ACT_RELU).view(B)
         return self._encode(video_features, text_features, 1, act=ops.ACT_RELU, taps=taps).view(B)

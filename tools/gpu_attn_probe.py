@@ -47,4 +47,4 @@ print(f"CTA 0: {n} items, {total} cycles = {total / max(n, 1):.0f} cycles/item")
 roles = {0: "softmax main q0 h0", 4: "softmax main q0 h1", 3: "softmax main q3 h0", 8: "leftover even h0", 9: "leftover odd h0",
          10: "loader", 11: "mma"}
 for w, name in roles.items():
-    print(f"  warp {w:2d} {name:20s} " + "  ".join(f"[{i}] {t[w * 8 + i] / max(n, 1):7.0f}" for i in range(4)) + "   cycles/item")
+    print(f"  warp {w:2d} {name:20s} " + "  ".join(f"[{i}] {t[w * 8 + i] / max(n, 1):6.0f}" for i in range(8)) + "   cycles/item")

@@ -53,11 +53,11 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 640;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, row-statistics; warps 4-19: epilogue
 constexpr int GEMM_EPI_WARPS = 16;  // four per TMEM lane quarter, each owning a quarter of the tile's columns
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : 6;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;  // a CTA pair splits the B tile between its two CTAs
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
   static constexpr int SLAB_BYTES = 32 * 32 * 2;  // one epilogue warp's 32-row x 32-column bf16 output slab (64B-swizzled)
   static constexpr int RN_BYTES = 2 * GEMM_BM * 8;  // (rstd, -rstd*mean) of the rows of two tiles in flight
@@ -206,12 +206,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int ro
   for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
-template <int BN, int EPI, typename OutT, bool LNIN>
+// CG = 1: one CTA per SM computes 128 x BN tiles. CG = 2: the two CTAs of a 2-cluster (one TPC) compute a 256 x BN tile
+// with ONE tcgen05.mma.cta_group::2 stream issued by the leader: each CTA stages its own 128 rows of A and half of the
+// B tile (a third less L2 -> shared-memory traffic per FLOP, half the B reads per MMA) and drains its own 128
+// accumulator rows.
+template <int BN, int EPI, typename OutT, bool LNIN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr bool TMA_STORE = (sizeof(OutT) == 2) && (EPI != EPI_BIAS_LN);
-  using Cfg = GemmCfg<BN>;
+  static_assert(CG == 1 || (CG == 2 && TMA_STORE), "CTA pairs are used with the TMA-store epilogues only");
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int WCOLS = BN / 4;      // columns of the tile owned by one epilogue warp
   constexpr int PIECES = WCOLS / 32;  // 32-column pieces per warp and tile
@@ -235,9 +240,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = p.N / BN;
-  const int n_tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int n_tiles = n_tiles_m * n_tiles_n;
   const int n_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  // work unit = CTA (CG = 1) or CTA pair (CG = 2); `row_off` = this CTA's rows inside the unit's M tile
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit = (CG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_units = (CG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int row_off = cta_rank * GEMM_BM;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -251,15 +262,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bar_tfull[a], 1);
-      mbar_init(&bar_tempty[a], GEMM_EPI_WARPS);
+      mbar_init(&bar_tempty[a], GEMM_EPI_WARPS * CG);  // CG = 2: the epilogue warps of both CTAs arrive on the leader's
       mbar_init(&bar_rnfull[a], 1);
       mbar_init(&bar_rnempty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrival / TMA credit
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -268,26 +283,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles_n) * GEMM_BM;
+      for (int t = unit; t < n_tiles; t += n_units) {
+        const int m0 = (t / n_tiles_n) * (GEMM_BM * CG) + row_off;
         const int n0 = (t % n_tiles_n) * BN;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
-          mbar_expect_tx(&bar_full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &bar_full[stage], kb * GEMM_BK, m0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &bar_full[stage], kb * GEMM_BK, n0);
+          if (CG == 2) {
+            // both CTAs' bytes are credited to the leader's barrier, which alone expects them
+            if (leader) mbar_expect_tx(&bar_full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+            tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &bar_full[stage], kb * GEMM_BK, m0);
+            tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &tmB, &bar_full[stage], kb * GEMM_BK, n0 + cta_rank * (BN / 2));
+          } else {
+            mbar_expect_tx(&bar_full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &bar_full[stage], kb * GEMM_BK, m0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &bar_full[stage], kb * GEMM_BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    // ------------------------------------------------------------------ MMA issuer (single thread; the pair's leader)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int t = unit; t < n_tiles; t += n_units, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&bar_tempty[as], aphase ^ 1);
@@ -300,13 +322,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16_ss(tmem_d, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2)
+              umma_bf16_ss_pair(tmem_d, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(tmem_d, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bar_empty[stage]);
+          if (CG == 2) umma_commit_pair(&bar_empty[stage]);  // frees the stage in both CTAs
+          else umma_commit(&bar_empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bar_tfull[as]);
+        if (CG == 2) umma_commit_pair(&bar_tfull[as]);  // each CTA's epilogue drains its own half
+        else umma_commit(&bar_tfull[as]);
       }
     }
   } else if (warp == 3) {
@@ -323,18 +351,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // narrow rows (C = 128 / 256): tiles are short, so the partials of tile i+1 are already in flight while tile i
         // is reduced (two register sets, loop unrolled by two)
         float2 ta[4][4], tb[4][4];
-        int t = blockIdx.x, it = 0;
-        if (t < n_tiles) stats_fetch<4, 4>(ta, p.in_stats, p.M, (t / n_tiles_n) * GEMM_BM, lane, 0);
+        int t = unit, it = 0;
+        if (t < n_tiles) stats_fetch<4, 4>(ta, p.in_stats, p.M, (t / n_tiles_n) * (GEMM_BM * CG) + row_off, lane, 0);
         while (t < n_tiles) {
-          int tn = t + gridDim.x;
-          if (tn < n_tiles) stats_fetch<4, 4>(tb, p.in_stats, p.M, (tn / n_tiles_n) * GEMM_BM, lane, 0);
+          int tn = t + n_units;
+          if (tn < n_tiles) stats_fetch<4, 4>(tb, p.in_stats, p.M, (tn / n_tiles_n) * (GEMM_BM * CG) + row_off, lane, 0);
           mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
           stats_reduce<4, 4>(ta, s_rn + (it & 1) * GEMM_BM, lane, 0, cw, p.K, p.in_eps);
           publish(it);
           t = tn; ++it;
           if (t >= n_tiles) break;
-          tn = t + gridDim.x;
-          if (tn < n_tiles) stats_fetch<4, 4>(ta, p.in_stats, p.M, (tn / n_tiles_n) * GEMM_BM, lane, 0);
+          tn = t + n_units;
+          if (tn < n_tiles) stats_fetch<4, 4>(ta, p.in_stats, p.M, (tn / n_tiles_n) * (GEMM_BM * CG) + row_off, lane, 0);
           mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
           stats_reduce<4, 4>(tb, s_rn + (it & 1) * GEMM_BM, lane, 0, cw, p.K, p.in_eps);
           publish(it);
@@ -342,8 +370,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         int it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-          const int m0 = (t / n_tiles_n) * GEMM_BM;
+        for (int t = unit; t < n_tiles; t += n_units, ++it) {
+          const int m0 = (t / n_tiles_n) * (GEMM_BM * CG) + row_off;
           float2* dst = s_rn + (it & 1) * GEMM_BM;
           if (n_chunks == 8) {
             float2 ta[4][8];
@@ -368,10 +396,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int part = (warp - 4) >> 2;  // which quarter of the tile's columns
     int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int t = unit; t < n_tiles; t += n_units, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (t / n_tiles_n) * GEMM_BM;
+      const int m0 = (t / n_tiles_n) * (GEMM_BM * CG) + row_off;
       const int n0 = (t % n_tiles_n) * BN;
       const int row_in_tile = q * 32 + lane;
       const int row = m0 + row_in_tile;
@@ -460,7 +488,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (pc + 1 == PIECES) {  // every tcgen05.ld of this warp for this tile has completed: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[as]);
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_leader(&bar_tempty[as]);  // the leader's MMA thread waits for both halves
+              else mbar_arrive(&bar_tempty[as]);
+            }
           }
           float v[32];
           epilogue_values<EPI, LNIN>(acc, n0 + col_in_tile, p, rn, res_cur, v);
@@ -513,18 +544,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // neither CTA may exit while its peer can still read its smem / signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI, typename OutT, bool LNIN>
+template <int BN, int EPI, typename OutT, bool LNIN, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, EPI, OutT, LNIN>;
+  using Cfg = GemmCfg<BN, CG>;
+  auto kern = gemm_tc_kernel<BN, EPI, OutT, LNIN, CG>;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -534,31 +567,59 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     }
     configured = true;
   }
-  const int n_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / BN);
-  int grid = sm_count();
-  if (n_tiles < grid) grid = n_tiles;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  const int n_tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * (p.N / BN);
+  int units = sm_count() / CG;
+  if (n_tiles < units) units = n_tiles;
+  if (CG == 1) {
+    kern<<<units, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(units * CG);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
+    if (e != cudaSuccess) {
+      set_error("cudaLaunchKernelEx(gemm_tc_kernel, cluster of %d): %s", CG, cudaGetErrorString(e));
+      return LRCE_ECUDA;
+    }
+  }
   return check_launch("gemm_tc_kernel");
 }
 
-template <int BN>
+// wave efficiency of `tiles` work units on `units` workers
+static double wave_eff(int tiles, int units) {
+  const int waves = (tiles + units - 1) / units;
+  return static_cast<double>(tiles) / (static_cast<double>(waves) * units);
+}
+
+template <int BN, int CG>
 static int dispatch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int epi,
                         int out_fp32, cudaStream_t stream) {
   const bool lnin = p.in_stats != nullptr;
-  if (out_fp32) {
-    LRCE_REQUIRE(epi == EPI_BIAS && !lnin, "fp32 output is only available with the plain bias epilogue (epi=%d)", epi);
-    return launch_gemm<BN, EPI_BIAS, float, false>(tmA, tmB, tmC, p, stream);
+  if constexpr (CG == 1) {
+    if (out_fp32) {
+      LRCE_REQUIRE(epi == EPI_BIAS && !lnin, "fp32 output is only available with the plain bias epilogue (epi=%d)", epi);
+      return launch_gemm<BN, EPI_BIAS, float, false, 1>(tmA, tmB, tmC, p, stream);
+    }
   }
   switch (epi) {
     case EPI_BIAS:
-      return lnin ? launch_gemm<BN, EPI_BIAS, bf16, true>(tmA, tmB, tmC, p, stream)
-                  : launch_gemm<BN, EPI_BIAS, bf16, false>(tmA, tmB, tmC, p, stream);
+      return lnin ? launch_gemm<BN, EPI_BIAS, bf16, true, CG>(tmA, tmB, tmC, p, stream)
+                  : launch_gemm<BN, EPI_BIAS, bf16, false, CG>(tmA, tmB, tmC, p, stream);
     case EPI_BIAS_GELU:
-      return lnin ? launch_gemm<BN, EPI_BIAS_GELU, bf16, true>(tmA, tmB, tmC, p, stream)
-                  : launch_gemm<BN, EPI_BIAS_GELU, bf16, false>(tmA, tmB, tmC, p, stream);
+      return lnin ? launch_gemm<BN, EPI_BIAS_GELU, bf16, true, CG>(tmA, tmB, tmC, p, stream)
+                  : launch_gemm<BN, EPI_BIAS_GELU, bf16, false, CG>(tmA, tmB, tmC, p, stream);
     case EPI_BIAS_RESIDUAL:
       LRCE_REQUIRE(!lnin, "the residual epilogue does not take a folded LayerNorm input");
-      return launch_gemm<BN, EPI_BIAS_RESIDUAL, bf16, false>(tmA, tmB, tmC, p, stream);
+      return launch_gemm<BN, EPI_BIAS_RESIDUAL, bf16, false, CG>(tmA, tmB, tmC, p, stream);
     default: break;
   }
   set_error("unknown GEMM epilogue %d", epi);
@@ -617,10 +678,16 @@ extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
                  "lrce_gemm_bf16: the LayerNorm epilogue needs N == 128, a bias and gamma/beta (N=%d)", N);
     rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, GEMM_BK, 128);
     if (rc != LRCE_OK) return rc;
-    return launch_gemm<128, EPI_BIAS_LN, bf16, false>(tmA, tmB, tmC, p, s);
+    return launch_gemm<128, EPI_BIAS_LN, bf16, false, 1>(tmA, tmB, tmC, p, s);
   }
   const bool wide = (N % 256 == 0);
-  rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, GEMM_BK, wide ? 256 : 128);
+  // CTA pairs (256 x 256 tiles on two SMs) for the compute-bound shapes, unless their wave quantisation is clearly worse
+  // than that of single-CTA 128 x 256 tiles
+  const int sms = sm_count();
+  const int tiles1 = ((M + 127) / 128) * (N / 256), tiles2 = ((M + 255) / 256) * (N / 256);
+  const bool pair = wide && !out_fp32 && K >= 256 && sms >= 2 && wave_eff(tiles2, sms / 2) >= wave_eff(tiles1, sms) - 0.02;
+  rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, GEMM_BK, wide ? (pair ? 128 : 256) : 128);
   if (rc != LRCE_OK) return rc;
-  return wide ? dispatch_epi<256>(tmA, tmB, tmC, p, epilogue, out_fp32, s) : dispatch_epi<128>(tmA, tmB, tmC, p, epilogue, out_fp32, s);
+  if (pair) return dispatch_epi<256, 2>(tmA, tmB, tmC, p, epilogue, out_fp32, s);
+  return wide ? dispatch_epi<256, 1>(tmA, tmB, tmC, p, epilogue, out_fp32, s) : dispatch_epi<128, 1>(tmA, tmB, tmC, p, epilogue, out_fp32, s);
 }

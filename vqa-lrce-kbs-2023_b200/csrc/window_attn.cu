@@ -263,6 +263,8 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     }
     // ---- pass 1: t = s * scale * log2e + bias (+ mask), maximum of this thread's 80 columns; t stays in registers.
     // Pad columns carry a bias of -inf (lrce_window_bias_pack), so they need no special case.
+    const bool timing = sh.prof != nullptr && blockIdx.x == 0 && lane == 0;
+    long long tc0 = timing ? clock64() : 0;
     float t[WA_HALF];
     float mx = -INFINITY;
     {
@@ -276,6 +278,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(sh.s_free);
+    if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 4] += tc - tc0; tc0 = tc; }  // [4] TMEM load of S
 #pragma unroll
     for (int c = 0; c < WA_HALF; c += 8) {
       const uint4 b4 = *reinterpret_cast<const uint4*>(bias_row + c);
@@ -290,9 +293,12 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
       }
     }
     sM[(mslot * 2 + half) * 160 + row] = mx;  // published before this warp's arrival on p_full(j)
+    if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 5] += tc - tc0; tc0 = tc; }  // [5] pass 1
     // P v of the previous item must have finished reading the P tile before it is refilled
     if (tile == 0 && j > 0) timed_wait(sh, sh.o_full, (j - 1) & 1, 1, j);
-    // ---- pass 2: p = exp2(t - max) -> bf16 A-operand tile
+    if (timing) tc0 = clock64();
+    // ---- pass 2: p = exp2(t - max) -> bf16 A-operand tile (fp32 exponent: the packed bf16x2 MUFU path was measured and
+    // is not faster here — the pass is issue-bound, not MUFU-bound — so the exact-argument form is kept)
 #pragma unroll
     for (int c = 0; c < WA_HALF; c += 8) {
       float p[8];
@@ -303,6 +309,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
       u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
       *reinterpret_cast<uint4*>(p_row + (c / 8) * 128) = u;
     }
+    if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 6] += tc - tc0; tc0 = tc; }  // [6] pass 2
     // ---- epilogue of the previous item of the main tile: must drain O before P v of THIS item overwrites it
     if (tile == 0 && j > 0) {
       // the partner published its maximum of item j-1 before arriving on p_full(j-1), and o_full(j-1) (waited above)
@@ -314,6 +321,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     fence_proxy_async_smem();  // P writes -> visible to the tensor core
     __syncwarp();
     if (lane == 0) mbar_arrive(sh.p_full);
+    if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 7] += tc - tc0; tc0 = tc; }  // [7] epilogue + fence
     if (tile == 0) {
       m_prev = mx; tok_prev = tok; seg_prev = seg; head_prev = head;
     } else {

@@ -44,7 +44,7 @@ _lib.lib().lrce_debug_attention_timing(0)
 t = buf.cpu().tolist()
 n, total = t[128], t[129]
 print(f"CTA 0: {n} items, {total} cycles = {total / max(n, 1):.0f} cycles/item")
-roles = {0: "softmax main q0 h0", 4: "softmax main q0 h1", 3: "softmax main q3 h0", 8: "leftover even h0", 9: "leftover odd h0",
+roles = {0: "softmax main q0 h0", 4: "softmax main q0 h1", 3: "softmax main q3 h0", 8: "leftover even h0", 9: "leftover odd h0", 14: "mma B (tile 1 PV)",
          10: "loader", 11: "mma"}
 for w, name in roles.items():
     print(f"  warp {w:2d} {name:20s} " + "  ".join(f"[{i}] {t[w * 8 + i] / max(n, 1):6.0f}" for i in range(8)) + "   cycles/item")

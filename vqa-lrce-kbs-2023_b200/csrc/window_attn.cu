@@ -13,7 +13,8 @@
 //                           the row index is window_source_token_377(), the function lrce_remap_index() exports for the
 //                           bit-exact test. v rows carry a 5th 16-byte chunk holding a constant 1 so that the P v product
 //                           also yields the softmax row sums.
-//   warp  11     MMA      : one thread issues S = q k^T (2 row tiles x [M=128, N=160, K=32]) and, per row tile, TWO
+//   warps 11,14  MMA      : one thread each (issuing 24 tcgen05.mma per item from ONE thread took ~2600 cycles and delayed
+//                           the P v results; warp 11 issues S and the row-tile-0 products, warp 14 the row-tile-1 products): S = q k^T (2 row tiles x [M=128, N=160, K=32]) and, per row tile, TWO
 //                           products O_A = P[:, 0:80] v[0:80], O_B = P[:, 80:160] v[80:160] ([M=128, N=48, K=80], v consumed
 //                           MN-major exactly as it sits in memory) with tcgen05.mma into TMEM
 //   warps 0-7    softmax  : rows 0..127 of the window (thread = row, warp w and w+4 split the 160 key columns in halves)
@@ -39,7 +40,7 @@ constexpr int WA_HALF = 80;         // key columns per softmax thread
 constexpr int WA_BIAS_PITCH = 160;  // dense bias row pitch (bf16) = key columns of the score tile
 constexpr int WA_VCH = 6;           // 16-byte chunks per staged v row: 4 of data, 1 with the constant 1, 1 of zeros
 constexpr int WA_ON = 8 * WA_VCH;   // N of the P v products (48)
-constexpr int WA_THREADS = 14 * 32;
+constexpr int WA_THREADS = 15 * 32;
 constexpr int WA_SOFTMAX_ARRIVALS = 12;  // 8 main warps + 2 leftover warps of the item + 2 leftover warps of the other parity
 
 // shared memory map (bytes)
@@ -388,12 +389,12 @@ window_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, co
       mbar_init(&sh.qk_full[b], 1);
       mbar_init(&sh.qk_empty[b], 1);
       mbar_init(&sh.v_full[b], 1);
-      mbar_init(&sh.v_empty[b], 1);
+      mbar_init(&sh.v_empty[b], 2);
     }
     mbar_init(sh.s_full, 1);
     mbar_init(sh.s_free, 10);  // 8 main warps + the 2 leftover warps of the item
     mbar_init(sh.p_full, WA_SOFTMAX_ARRIVALS);
-    mbar_init(sh.o_full, 1);
+    mbar_init(sh.o_full, 2);  // one tcgen05.commit from each of the two MMA issuers
     fence_barrier_init();
   }
   if (warp == 10) tmem_alloc(tmem_slot, WA_TM_COLS);
@@ -508,12 +509,29 @@ window_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, co
                                            /*lbo: key groups*/ WA_VCH * 128, /*sbo: dim groups*/ 128);
         const uint64_t dp = umma_desc_nosw(smem0 + WA_OFF_P, 128, (WA_KEYS / 8) * 128);
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile)
+        for (int kk = 0; kk < WA_KEYS / 16; ++kk)  // row tile 0; row tile 1 is issued by warp 14
+          umma_bf16_ss(tmem_base + WA_TM_O + (kk >= WA_HALF / 16 ? 1 : 0) * WA_ON, dp + ((kk * 256) >> 4),
+                       dv + ((kk * (2 * WA_VCH * 128)) >> 4), idesc_o, (kk % (WA_HALF / 16)) != 0);
+        umma_commit(sh.o_full);
+        umma_commit(&sh.v_empty[j & 1]);
+      }
+    }
+  } else if (warp == 14) {
+    // ===================================================================== second MMA issuer: P v of row tile 1
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, WA_ON) | (1u << 16);  // B (= v) MN-major
+      const uint32_t smem0 = smem_u32(smem);
+      for (int j = 0; j < n_my; ++j) {
+        timed_wait(sh, sh.p_full, j & 1, 2, j);
+        timed_wait(sh, &sh.v_full[j & 1], (j >> 1) & 1, 3, j);
+        tcgen05_fence_after();
+        const uint64_t dv = umma_desc_nosw(smem0 + WA_OFF_QKV + (j & 1) * WA_QKV_BYTES + WA_Q_BYTES + WA_K_BYTES,
+                                           /*lbo: key groups*/ WA_VCH * 128, /*sbo: dim groups*/ 128);
+        const uint64_t dp = umma_desc_nosw(smem0 + WA_OFF_P + WA_P_TILE_BYTES, 128, (WA_KEYS / 8) * 128);
 #pragma unroll
-          for (int kk = 0; kk < WA_KEYS / 16; ++kk)
-            umma_bf16_ss(tmem_base + WA_TM_O + (tile * 2 + (kk >= WA_HALF / 16 ? 1 : 0)) * WA_ON,
-                         dp + ((tile * WA_P_TILE_BYTES + kk * 256) >> 4), dv + ((kk * (2 * WA_VCH * 128)) >> 4), idesc_o,
-                         (kk % (WA_HALF / 16)) != 0);
+        for (int kk = 0; kk < WA_KEYS / 16; ++kk)
+          umma_bf16_ss(tmem_base + WA_TM_O + (2 + (kk >= WA_HALF / 16 ? 1 : 0)) * WA_ON, dp + ((kk * 256) >> 4),
+                       dv + ((kk * (2 * WA_VCH * 128)) >> 4), idesc_o, (kk % (WA_HALF / 16)) != 0);
         umma_commit(sh.o_full);
         umma_commit(&sh.v_empty[j & 1]);
       }

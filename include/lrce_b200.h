@@ -46,9 +46,9 @@ const char* lrce_last_error(void);
  * nn.TransformerDecoderLayer built at fusionv3.py:8-17.
  *
  * LayerNorm folding (norm1 -> qkv, norm2 -> fc1; video_swin_ori.py:252,:285): instead of a separate LayerNorm pass,
- *  - a producing GEMM called with out_stats != NULL also writes float2 out_stats[N/cw][M] = (mean, M2) of every
+ *  - a producing GEMM called with out_stats != NULL also writes float2 out_stats[M][N/cw] = (mean, M2) of every
  *    cw-column chunk of the rows it stores (taken just before the bf16 rounding); cw = 64 when N % 256 == 0, else 32;
- *  - a consuming GEMM called with in_stats != NULL (float2 [K/in_chunk][M], in_chunk = the producer's cw, at most 16
+ *  - a consuming GEMM called with in_stats != NULL (float2 [M][K/in_chunk] — row-major, so a row range of the matrix owns a contiguous range of statistics —, in_chunk = the producer's cw, 4, 8 or 16
  *    chunks) takes A = the RAW rows, W = W * diag(gamma),
  *    in_colsum[n] = sum_k W'[n,k], bias = bias + W beta, and computes
  *    out[m,n] = epilogue(rstd[m] * (acc[m,n] - mean[m] * in_colsum[n]) + bias[n]) with (mean, rstd) of row m rebuilt

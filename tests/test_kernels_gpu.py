@@ -73,14 +73,14 @@ def test_window_remap_tensor_bit_exact(ops, name, C):
 
 
 def chunk_stats(x):
-    """torch statement of the LayerNorm partials a producing GEMM emits: (M, C) bf16 -> fp32 [C/cw, M, 2] = (mean, M2),
+    """torch statement of the LayerNorm partials a producing GEMM emits: (M, C) bf16 -> fp32 [M, C/cw, 2] = (mean, M2),
     cw = 64 columns when C % 256 == 0, else 32 (ops.stats_chunk)"""
     M, C = x.shape
     cw = 64 if C % 256 == 0 else 32
     v = x.float().view(M, C // cw, cw)
     mean = v.mean(-1)
     m2 = ((v - mean[..., None]) ** 2).sum(-1)
-    return torch.stack([mean, m2], -1).permute(1, 0, 2).contiguous()
+    return torch.stack([mean, m2], -1).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -122,7 +122,7 @@ def test_gemm_emits_row_statistics(ops, M, N, K, epi):
         ref = a.float() @ w.float().t() + b
     assert rel_l2(y, ref) < 6e-3
     want = chunk_stats(y)  # the kernel takes them just before the bf16 rounding of y: equal up to the rounding noise
-    got = st.view(N // ops.stats_chunk(N), M, 2)
+    got = st.view(M, N // ops.stats_chunk(N), 2)
     assert (got[..., 0] - want[..., 0]).abs().max().item() < 2e-3 * max(1.0, y.float().abs().max().item())
     assert ((got[..., 1] - want[..., 1]).abs() / want[..., 1].clamp_min(1e-3)).max().item() < 2e-2
 

@@ -39,11 +39,11 @@ struct GemmParams {
   //   out[m, n] = rstd[m] * (acc[m, n] - mean[m] * colsum[n]) + bias'[n]
   // with (mean, rstd) of row m rebuilt from the per-64-column partials `in_stats` the producing GEMM emitted,
   // colsum[n] = sum_k W'[n, k] and bias' = bias + W beta (both prepared once at weight-pack time).
-  const float* in_stats;   // float2 [K/in_chunk][M]: (mean, M2) of each in_chunk-column chunk of row m (<= 16 chunks)
+  const float* in_stats;   // float2 [M][K/in_chunk]: (mean, M2) of each in_chunk-column chunk of row m (4, 8 or 16 chunks)
   int in_chunk;            // 32 or 64
   const float* in_colsum;  // [N]
   float in_eps;
-  float* out_stats;  // nullptr, or float2 [N/cw][M]: (mean, M2) of every cw-column chunk of the output rows, cw = 32 for
+  float* out_stats;  // nullptr, or float2 [M][N/cw]: (mean, M2) of every cw-column chunk of the output rows, cw = 32 for
                      // the 128-wide tile kernels (N % 256 != 0) and 64 otherwise (taken before the bf16 rounding: the
                      // rounding noise shifts the mean by ~2^-9 rms / sqrt(cw), far below bf16)
 };
@@ -100,9 +100,13 @@ __device__ __forceinline__ void stats_fetch(float2 (&t)[ROWS][NC], const float* 
 #pragma unroll
   for (int i = 0; i < ROWS; ++i) {
     const int row = min(m0 + lane + 32 * (i0 + i), M - 1);  // tail rows of the last tile read a valid row, never stored
-    const float2* st = reinterpret_cast<const float2*>(stats) + row;
+    const float4* st = reinterpret_cast<const float4*>(stats) + static_cast<size_t>(row) * (NC / 2);  // NC float2 per row
 #pragma unroll
-    for (int c = 0; c < NC; ++c) t[i][c] = __ldg(&st[static_cast<size_t>(c) * M]);
+    for (int c = 0; c < NC; c += 2) {
+      const float4 v = __ldg(st + c / 2);
+      t[i][c] = make_float2(v.x, v.y);
+      t[i][c + 1] = make_float2(v.z, v.w);
+    }
   }
 }
 template <int NC, int ROWS>
@@ -447,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = o4[j];
           if (p.out_stats != nullptr)
-            reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(part) * p.M + row] = stats32(y);
+            reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(row) * (BN / 32) + part] = stats32(y);
         }
       } else if constexpr (TMA_STORE) {
         // Each warp owns WCOLS columns of its 32 rows, in 32-column pieces: tcgen05.ld -> math -> private 64B-swizzled
@@ -501,11 +505,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float2 st_piece = stats32(v);
             if (PIECES == 1) {  // 128-wide tiles: 32-column chunks
               if (row < p.M)
-                reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>((n0 + col_in_tile) >> 5) * p.M + row] = st_piece;
+                reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(row) * (p.N >> 5) + ((n0 + col_in_tile) >> 5)] = st_piece;
             } else if (pc == 0) {
               st_carry = st_piece;
             } else if (row < p.M) {  // 256-wide tiles: this warp's two pieces form one 64-column chunk
-              reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>((n0 + part * WCOLS) >> 6) * p.M + row] =
+              reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(row) * (p.N >> 6) + ((n0 + part * WCOLS) >> 6)] =
                   stats_merge(st_carry, st_piece, 32.0f);
             }
           }
@@ -648,7 +652,7 @@ extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   if (in_stats != nullptr)
     LRCE_REQUIRE(in_colsum && bias && (in_chunk == 32 || in_chunk == 64) && K % in_chunk == 0 &&
                      (K / in_chunk == 4 || K / in_chunk == 8 || K / in_chunk == 16) && (reinterpret_cast<uintptr_t>(in_colsum) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(in_stats) & 7) == 0,
+                     (reinterpret_cast<uintptr_t>(in_stats) & 15) == 0,
                  "lrce_gemm_bf16: a folded LayerNorm input needs statistics in 4, 8 or 16 chunks of 32 or 64 columns, column sums and a bias (K=%d, chunk=%d)", K, in_chunk);
   if (out_stats != nullptr)
     LRCE_REQUIRE(!out_fp32 && (reinterpret_cast<uintptr_t>(out_stats) & 7) == 0,

@@ -7,12 +7,18 @@ natural token order ``[segment, d, h, w, C]`` flattened to ``[M, C]`` for the wh
 ``b c d h w <-> b d h w c`` ping-pong (video_swin_ori.py:428,439,683,685), its window partition/roll copies and its
 per-segment Python loop (video.py:33) do not exist here.
 """
+import os
+
 import torch
 from torch import nn
 
 from . import ops
 
 SWIN_CKPT = "./pretrained_models/swin_base_patch244_window877_kinetics600_22k.pth"  # e2e.py:11
+# Segments per L2-resident slab for stages 1..4 (0 = whole batch); LRCE_B200_SLABS="a,b,c,d" overrides. Measured on B200 at
+# batch 32 (profiles/README.md): 0,0,0,0 -> 19.8 ms; 12,48,0,0 -> 19.6 ms; 6,24,0,0 -> 20.2 ms; 4,16,0,0 -> 20.9 ms — the HBM
+# traffic saved is paid back in per-launch fill/drain, so whole-batch execution stays the default.
+SLAB_SEGMENTS = tuple(int(v) for v in os.environ.get("LRCE_B200_SLABS", "0,0,0,0").split(","))
 
 
 def _relative_position_index(window=(8, 7, 7)):
@@ -185,35 +191,56 @@ class SwinTransformer3D(nn.Module):
         if D != 3 or H % 7 or W % 7:
             raise ops._lib.LrceError("the window-attention kernel needs 5/6-frame segments and H, W multiples of 28")
         a = ops.patch_gather(clips)
-        M = a.shape[0]
-        # per-row LayerNorm partials (mean, M2 per 64-column chunk) travel from each GEMM that writes the residual
-        # stream to the next GEMM that reads it through a LayerNorm; two buffers alternate (norm1 / norm2)
-        st_a = torch.empty(M * self.embed_dim // 16, device=a.device, dtype=torch.float32)  # >= [C/chunk, M, 2] at any stage
-        st_b = torch.empty_like(st_a)
-        x = ops.gemm(a, pk["pe_w"], pk["pe_b"], epilogue=ops.EPI_BIAS_LN, ln=(pk["pe_g"], pk["pe_beta"], 1e-5), stats_out=st_a)
-        if taps is not None:
-            taps["patch_embed"] = x.view(n, D, H, W, -1).clone()
+        dev = a.device
         C = self.embed_dim
+        # Optional depth-first execution over slabs of whole segments (SLAB_SEGMENTS): a segment never interacts with another
+        # one inside Swin (windows do not cross segments), so a slab can run patch-embed, the stage's blocks and the merging
+        # back to back while its activations are still in the 126 MB L2. `taps` (tests) forces whole-batch execution.
+        slabs = [0, 0, 0, 0] if taps is not None else list(SLAB_SEGMENTS)
+        x_in, st_in = None, None  # stage input over all segments + its row-major LayerNorm partials
         for i, st in enumerate(pk["stages"]):
             heads = self.num_heads[i]
             shift = (3, 3) if H > 7 else (0, 0)  # clamped axes are never shifted (video_swin_ori.py:91-104)
-            for j, b in enumerate(st["blocks"]):
-                qkv = ops.gemm(x, b["wqkv"], b["bqkv"], ln_in=(st_a, b["cqkv"], 1e-5))
-                att = ops.window_attention(qkv, b["bias"], n, D, H, W, C, heads, shift if j % 2 else (0, 0))
-                del qkv
-                ops.gemm(att, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_b)
-                del att
-                hid = ops.gemm(x, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU, ln_in=(st_b, b["c1"], 1e-5))
-                ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_a)
-                del hid
-                if taps is not None and j < 2 and i < 3:
-                    taps[f"stage{i}.block{j}"] = x.view(n, D, H, W, C).clone()
-            if st["ds"] is not None:
-                y = ops.patch_merge_ln(x, st["ds"]["g"], st["ds"]["b"], 1e-5, n, D, H, W, C)
-                x = ops.gemm(y, st["ds"]["w"], None, stats_out=st_a)
+            rps = D * H * W  # rows per segment
+            nc = C // ops.stats_chunk(C)  # (mean, M2) partials per row
+            G = slabs[i] if 0 < slabs[i] < n else n
+            last = st["ds"] is None
+            if not last:
+                x_out = torch.empty((n * rps // 4, 2 * C), device=dev, dtype=torch.bfloat16)
+                st_out = torch.empty(n * (rps // 4) * (2 * C // ops.stats_chunk(2 * C)) * 2, device=dev, dtype=torch.float32)
+            for s0 in range(0, n, G):
+                ns = min(G, n - s0)
+                r0, r1 = s0 * rps, (s0 + ns) * rps
+                st_b = torch.empty(ns * rps * nc * 2, device=dev, dtype=torch.float32)
+                if i == 0:
+                    st_a = torch.empty_like(st_b)
+                    x = ops.gemm(a[r0:r1], pk["pe_w"], pk["pe_b"], epilogue=ops.EPI_BIAS_LN,
+                                 ln=(pk["pe_g"], pk["pe_beta"], 1e-5), stats_out=st_a)
+                    if taps is not None:
+                        taps["patch_embed"] = x.view(n, D, H, W, -1).clone()
+                else:
+                    x, st_a = x_in[r0:r1], st_in[r0 * nc * 2:r1 * nc * 2]
+                for j, b in enumerate(st["blocks"]):
+                    qkv = ops.gemm(x, b["wqkv"], b["bqkv"], ln_in=(st_a, b["cqkv"], 1e-5))
+                    att = ops.window_attention(qkv, b["bias"], ns, D, H, W, C, heads, shift if j % 2 else (0, 0))
+                    del qkv
+                    ops.gemm(att, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_b)
+                    del att
+                    hid = ops.gemm(x, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU, ln_in=(st_b, b["c1"], 1e-5))
+                    ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_a)
+                    del hid
+                    if taps is not None and j < 2 and i < 3:
+                        taps[f"stage{i}.block{j}"] = x.view(n, D, H, W, C).clone()
+                if not last:
+                    y = ops.patch_merge_ln(x, st["ds"]["g"], st["ds"]["b"], 1e-5, ns, D, H, W, C)
+                    nc2 = 2 * C // ops.stats_chunk(2 * C)
+                    ops.gemm(y, st["ds"]["w"], None, out=x_out[r0 // 4:r1 // 4], stats_out=st_out[(r0 // 4) * nc2 * 2:(r1 // 4) * nc2 * 2])
+                    del y
+            if not last:
+                x_in, st_in = x_out, st_out
                 H, W, C = H // 2, W // 2, 2 * C
             if taps is not None:
-                taps[f"stage{i}.out"] = x.view(n, D, H, W, C).clone()
+                taps[f"stage{i}.out"] = (x if last else x_in).view(n, D, H, W, C).clone()
         out = ops.layernorm(x, pk["norm_g"], pk["norm_b"], 1e-5, out_fp32=out_fp32)
         return out.view(n, D, H, W, C)
 

@@ -59,8 +59,8 @@ def stats_chunk(width):
 def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, residual=None, out=None, out_fp32=False, ln=None, ln_in=None,
          stats_out=None):
     """out = epilogue(a @ w.T); a (M,K) bf16 with unit inner stride, w (N,K) bf16; see lrce_gemm_bf16.
-    ln_in = (stats fp32 [K/cw, M, 2], colsum fp32 [N], eps): LayerNorm folded into the A operand (w, bias pre-folded);
-    stats_out = fp32 [N/cw, M, 2] buffer that receives the (mean, M2) partials of the rows written.
+    ln_in = (stats fp32 [M, K/cw, 2], colsum fp32 [N], eps): LayerNorm folded into the A operand (w, bias pre-folded);
+    stats_out = fp32 [M, N/cw, 2] buffer that receives the (mean, M2) partials of the rows written.
     cw = stats_chunk(width) of the PRODUCING GEMM: 64 columns when its N % 256 == 0, else 32."""
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(bias, torch.float32, "bias")
     _req(residual, torch.bfloat16, "residual")

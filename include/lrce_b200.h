@@ -94,9 +94,10 @@ int lrce_remap_index(int* gather, int* region, int* relpos, int D, int H, int W,
 
 /* ---- window attention ------------------------------------------------------------------------------------------ */
 
-/* bias_dense bf16 [n_heads, 147, 160] = relative_position_bias_table[index(i,j)][h] * log2(e), columns in the attention
- * kernel's key order (keys grouped by shift-mask class, 13 pad columns = -inf; csrc/remap.cuh key_slot_377), from
- * table fp32 [2535, n_heads]; done once per weight load. Replaces the gather at video_swin_ori.py:171-173. */
+/* bias_dense bf16 [n_heads, 160, 160] = relative_position_bias_table[index(i,j)][h] * log2(e), rows and columns in the
+ * attention kernel's slot order (tokens grouped by shift-mask class, 13 pad slots; pad columns = -inf; csrc/remap.cuh
+ * key_slot_377); rows 155-156 of every head hold float[160] row maxima. From table fp32 [2535, n_heads]; done once per
+ * weight load. Replaces the gather at video_swin_ori.py:171-173. */
 int lrce_window_bias_pack(const float* table, void* bias_dense, int n_heads, void* stream);
 
 /* out[n_seg*D*H*W, C] = merge_heads(softmax(q k^T / sqrt(32) + bias + shift_mask) v) per (3,7,7) window, with the cyclic
@@ -107,7 +108,7 @@ int lrce_window_attention_bf16(const void* qkv, void* out, const void* bias_dens
                                int n_heads, int shift_h, int shift_w, void* stream);
 
 /* profiling hook: per-warp mbarrier-wait cycle counters of CTA 0 of later lrce_window_attention_bf16 launches are
- * accumulated into buf (device, 16*8+3 int64, zeroed by the caller; layout in csrc/window_attn.cu); NULL switches it off. */
+ * accumulated into buf (device, 224 int64, zeroed by the caller; layout in csrc/window_attn.cu); NULL switches it off. */
 int lrce_debug_attention_timing(long long* buf);
 
 /* ---- recurrent cross-modal encoder ------------------------------------------------------------------------------ */

@@ -36,15 +36,15 @@ hw, C, heads = 14, 512, 16
 T = 3 * hw * hw
 qkv = torch.randn(n_seg * T, 3 * C, device="cuda").bfloat16()
 bias = ops.window_bias_pack(torch.randn(2535, heads, device="cuda") * 0.5)
-buf = torch.zeros(16 * 8 + 4 + 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(224, dtype=torch.int64, device="cuda")
 _lib.lib().lrce_debug_attention_timing(buf.data_ptr())
 ops.window_attention(qkv, bias, n_seg, 3, hw, hw, C, heads, (3, 3))
 torch.cuda.synchronize()
 _lib.lib().lrce_debug_attention_timing(0)
 t = buf.cpu().tolist()
-n, total = t[128], t[129]
+n, total = t[192], t[193]
 print(f"CTA 0: {n} items, {total} cycles = {total / max(n, 1):.0f} cycles/item")
-roles = {0: "softmax main q0 h0", 4: "softmax main q0 h1", 3: "softmax main q3 h0", 8: "leftover even h0", 9: "leftover odd h0", 14: "mma B (tile 1 PV)",
-         10: "loader", 11: "mma"}
+roles = {0: "main q0 c0", 4: "main q0 c1", 15: "main q3 c3", 16: "leftover even h0", 17: "leftover odd h0", 18: "loader",
+         19: "mma A (tile 0)", 22: "mma B (tile 1)"}
 for w, name in roles.items():
     print(f"  warp {w:2d} {name:20s} " + "  ".join(f"[{i}] {t[w * 8 + i] / max(n, 1):6.0f}" for i in range(8)) + "   cycles/item")

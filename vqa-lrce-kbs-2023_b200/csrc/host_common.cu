@@ -108,6 +108,45 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return LRCE_OK;
 }
 
+int make_tmap_nd_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes, int l2_promo_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available from the driver");
+    return LRCE_EDRIVER;
+  }
+  if (rank < 1 || rank > 5 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA operand must be 16-byte aligned, rank 1..5 (base=%p rank=%d)", base, rank);
+    return LRCE_EINVAL;
+  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) {
+      st[i] = strides_bytes[i];
+      if (st[i] & 15) {
+        set_error("TMA strides must be multiples of 16 bytes (stride %d = %llu)", i, (unsigned long long)st[i]);
+        return LRCE_EINVAL;
+      }
+    }
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUtensorMapL2promotion pr = l2_promo_bytes == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                    : l2_promo_bytes == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                    : l2_promo_bytes == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, st, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+    return LRCE_EDRIVER;
+  }
+  return LRCE_OK;
+}
+
 }  // namespace lrce
 
 extern "C" const char* lrce_last_error(void) { return lrce::last_error(); }

@@ -21,6 +21,11 @@ int check_launch(const char* what);
 int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer, int swizzle_bytes = 128);
 
+// N-D (rank <= 5) bf16 tensor map: dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of dims[i+1];
+// swizzle_bytes in {0, 64, 128}; l2_promo_bytes in {0, 64, 128, 256}.
+int make_tmap_nd_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes, int l2_promo_bytes);
+
 int sm_count();
 
 }  // namespace lrce

@@ -65,6 +65,19 @@ __host__ __device__ inline int key_slot_377(int tok) {
   const int base = ch ? (cw ? 128 : 88) : (cw ? 48 : 0);
   return base + idx;
 }
+// inverse of key_slot_377: window token of row / key slot `slot` (0..159), -1 for the 13 pad slots. Inside a class the slots
+// run (d, h', w') with w' fastest, which is exactly the order in which a TMA box (32 channels, w-part, h-part, 3 frames)
+// lands in shared memory: the attention kernel loads each class with ONE box per operand.
+__host__ __device__ inline int slot_token_377(int slot) {
+  const int cls = (slot >= 48) + (slot >= 88) + (slot >= 128);
+  const bool ch = cls >= 2, cw = (cls & 1) != 0;
+  const int base = ch ? (cw ? 128 : 88) : (cw ? 48 : 0);
+  const int nh_c = ch ? 3 : 4, nw_c = cw ? 3 : 4;
+  const int idx = slot - base;
+  if (idx >= 3 * nh_c * nw_c) return -1;
+  const int w = idx % nw_c, h = (idx / nw_c) % nh_c, d = idx / (nw_c * nh_c);
+  return d * 49 + (h + (ch ? 4 : 0)) * 7 + w + (cw ? 4 : 0);
+}
 // mask class of the 8-column group `grp` (0..19) of the score tile
 __host__ __device__ inline int key_group_class_377(int grp) { return (grp >= 6) + (grp >= 11) + (grp >= 16); }
 

@@ -148,12 +148,12 @@ def remap_index(dims, window, shift, device="cuda"):
 
 
 def window_bias_pack(table):
-    """relative_position_bias_table fp32 [2535, nH] -> dense bf16 [nH, 147, 160] (pre-multiplied by log2 e; columns in the
-    kernel's class-grouped key order, pad columns -inf)."""
+    """relative_position_bias_table fp32 [2535, nH] -> dense bf16 [nH, 160, 160] (pre-multiplied by log2 e; rows and columns
+    in the kernel's class-grouped slot order, pad columns -inf; rows 155-156 hold the fp32 row maxima)."""
     _req(table, torch.float32, "table")
     assert table.is_contiguous() and table.shape[0] == 2535
     nh = table.shape[1]
-    out = torch.empty((nh, 147, BIAS_PITCH), device=table.device, dtype=torch.bfloat16)
+    out = torch.empty((nh, BIAS_PITCH, BIAS_PITCH), device=table.device, dtype=torch.bfloat16)
     _call("lrce_window_bias_pack", _ptr(table), _ptr(out), nh, _stream())
     return out
 

@@ -54,15 +54,34 @@ def load_peaks():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)"""
+    """samples SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line). In-process NVML
+    (nvidia_ml_py) every 5 ms on a thread, so even a 100 ms timed region gets samples; `nvidia-smi -lms` as a fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.sm, self.mx, self.power, self.reasons = [], [], [], set()
 
     def start(self):
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            try:  # honour CUDA_VISIBLE_DEVICES remapping
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -70,11 +89,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.reasons |= {name for bit, name in self.BITS.items() if r & bit}
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(sm),
+                    "power_w": round(sorted(self.power)[len(self.power) // 2], 1) if self.power else None, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,7 +123,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def model_kwargs(cfg):

@@ -44,7 +44,7 @@ _lib.lib().lrce_debug_attention_timing(0)
 t = buf.cpu().tolist()
 n, total = t[192], t[193]
 print(f"CTA 0: {n} items, {total} cycles = {total / max(n, 1):.0f} cycles/item")
-roles = {0: "main q0 c0", 4: "main q0 c1", 15: "main q3 c3", 16: "leftover even h0", 17: "leftover odd h0", 18: "loader",
-         19: "mma A (tile 0)", 22: "mma B (tile 1)"}
+roles = {0: "softmax t0 q0 c0", 5: "softmax t0 q1 c1", 15: "softmax t0 q3 c3", 16: "softmax t1 q0", 19: "softmax t1 q3", 20: "loader",
+         21: "mma tile 0", 22: "mma tile 1"}
 for w, name in roles.items():
     print(f"  warp {w:2d} {name:20s} " + "  ".join(f"[{i}] {t[w * 8 + i] / max(n, 1):6.0f}" for i in range(8)) + "   cycles/item")

@@ -21,9 +21,8 @@
 //                           below), double-buffered, completion on mbarriers.
 //   warps 21,22  MMA      : one thread each, row tile 0 (slots 0..127) / row tile 1 (slots 128..159):
 //                           S = q k^T [M=128, N=160, K=32] (both operands K-major, 64B swizzle), then O = P v
-//                           [M=128, N=32, K=160] (v consumed MN-major exactly as TMA delivered it) and L = P 1
-//                           [M=128, N=16, K=160] (row sums of the bf16-rounded probabilities). Accumulators in TMEM:
-//                           S0, S1 (2 x 160 columns), O/L double-buffered per tile (4 x 48 columns) = 512.
+//                           [M=128, N=32, K=160] (v consumed MN-major exactly as TMA delivered it). Accumulators in
+//                           TMEM: S0, S1 (2 x 160 columns), O double-buffered per tile (4 x 32 columns).
 //   warps 0-15   softmax  : row tile 0, four warps per TMEM lane quarter (thread = row, warp = 40 key columns).
 //   warps 16-19  softmax  : row tile 1. Its 32 slots are loaded FOUR times into the q tile, so every TMEM lane quarter of
 //                           S1 holds the same 32 rows and warp 16+i (lane quarter i) takes key columns [40 i, 40 i + 40):
@@ -33,8 +32,11 @@
 // memory and a 128-thread named barrier; max_j bias_ij precomputed per row by lrce_window_bias_pack) — softmax is
 // invariant to the shift, the shift mask only lowers scores, and bf16 probabilities keep their relative precision under
 // a bound that is loose by a few units. Then p = exp2(s * scale*log2e + bias + mask - m) straight into bf16 A-operand
-// tiles (double-buffered, so no warp ever waits for P v of the previous unit), and the epilogue of unit j-1 (O / L from
-// TMEM, 16-byte stores through the inverse remap) runs after the probabilities of unit j are handed to the tensor core.
+// tiles (double-buffered, so no warp ever waits for P v of the previous unit); every warp also sums its 40 probabilities
+// and parks the partial row sum where the other warps of the row find it one unit later (row tile 0: a TMEM column of
+// the shared lane quarter via tcgen05.st; row tile 1: shared memory), ordered by the next unit's maximum-exchange barrier.
+// The epilogue of unit j-1 (O from TMEM, 1 / row sum, 16-byte stores through the inverse remap) runs after the
+// probabilities of unit j are handed to the tensor core.
 // The S accumulator is released as soon as a warp has its 40 scores in registers, so S(j+1) is computed under the
 // softmax of unit j.
 #include "host_common.h"
@@ -47,7 +49,7 @@ constexpr int WA_N = 147;           // tokens per (3,7,7) window
 constexpr int WA_KEYS = 160;        // row / key slots of a window (class-grouped, 13 pads)
 constexpr int WA_QCOLS = 40;        // key columns per softmax thread
 constexpr int WA_BIAS_PITCH = 160;  // dense bias row pitch (bf16) = key columns of the score tile
-constexpr int WA_ON = 48;           // TMEM columns of one output buffer: 32 dims + 16 row-sum columns
+constexpr int WA_ON = 32;           // TMEM columns of one output buffer (head_dim)
 constexpr int WA_THREADS = 24 * 32;
 constexpr int WA_SOFTMAX_THREADS = 20 * 32;
 constexpr int WA_WARP_LOADER = 20, WA_WARP_MMA0 = 21, WA_WARP_MMA1 = 22, WA_WARP_TMEM = 23;
@@ -68,17 +70,17 @@ constexpr int WA_OFF_P0 = 2 * WA_STAGE_BYTES;
 constexpr int WA_OFF_P1 = WA_OFF_P0 + 2 * WA_P0_BYTES;
 constexpr int WA_OFF_BIAS = WA_OFF_P1 + 2 * WA_P1_BYTES;
 constexpr int WA_OFF_BMAX = WA_OFF_BIAS + WA_BIAS_ROWS * WA_BIAS_PITCH * 2;
-constexpr int WA_OFF_ONES = WA_OFF_BIAS + WA_BIAS_COPY_BYTES;  // 16 x 16 bf16 ones (B operand of L = P 1), 512 B
-constexpr int WA_OFF_BAR = WA_OFF_ONES + 512;                  // mbarriers, TMEM slot, watchdog flag: 256 B
+constexpr int WA_OFF_BAR = WA_OFF_BIAS + WA_BIAS_COPY_BYTES;   // mbarriers, TMEM slot, watchdog flag: 192 B
+constexpr int WA_OFF_SUM1 = WA_OFF_BAR + 192;  // float [2][3][32]: partial row sums of row tile 1 (warps 17..19 -> warp 16)
 constexpr int WA_OFF_M = WA_OFF_BIAS + WA_BIAS_HEAD_BYTES;     // float [2][4][128] + [2][4][32]: partial raw-score maxima
 constexpr int WA_SMEM = WA_OFF_M + (2 * 4 * 128 + 2 * 4 * 32) * 4;
-static_assert(WA_OFF_BAR + 256 <= WA_OFF_M, "barrier block must fit behind the bias rows");
+static_assert(WA_OFF_SUM1 + 2 * 3 * 32 * 4 <= WA_OFF_M, "barrier block and tile-1 sums must fit behind the bias rows");
 static_assert(WA_SMEM <= 227 * 1024, "window attention shared-memory budget");
 static_assert(WA_OFF_P1 + WA_P1_BYTES + 128 * WA_KEYS * 2 <= WA_SMEM, "row tile 1's A operand must stay inside shared memory");
 
 // TMEM columns
-constexpr int WA_TM_S0 = 0, WA_TM_S1 = 160, WA_TM_O0 = 320, WA_TM_O1 = 416, WA_TM_COLS = 512;
-static_assert(WA_TM_O1 + 2 * WA_ON <= WA_TM_COLS, "TMEM budget");
+constexpr int WA_TM_S0 = 0, WA_TM_S1 = 160, WA_TM_O0 = 320, WA_TM_O1 = 384, WA_TM_SUM = 448, WA_TM_COLS = 512;
+static_assert(WA_TM_O1 + 2 * WA_ON <= WA_TM_SUM && WA_TM_SUM + 8 <= WA_TM_COLS, "TMEM budget");  // SUM: [2 slots][4 warps]
 
 constexpr uint32_t WA_QK_TX_BYTES = (WA_N + 3 * 27) * 64 + WA_N * 64;  // q (class 3 four times) + k
 constexpr uint32_t WA_V_TX_BYTES = WA_N * 64;
@@ -129,6 +131,16 @@ __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
   return v;
 }
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -161,15 +173,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// mbarrier wait that also accounts the stall to counter `slot` of this warp when the profiling hook is armed. With the
-// hook armed it doubles as a watchdog: a wait longer than ~50 ms records (warp, slot, item) in prof[196..] and raises
-// a CTA-wide abort flag that makes every later wait fall through, so a protocol deadlock ends with a report, not a hang.
+// mbarrier wait. PROF (profiling hook armed): accounts the stall to counter `slot` of this warp and doubles as a watchdog —
+// a wait longer than ~50 ms records (warp, slot, item) in prof[196..] and raises a CTA-wide abort flag that makes every
+// later wait fall through, so a protocol deadlock ends with a report, not a hang. Production: parked wait, no spinning.
+template <bool PROF>
 __device__ __forceinline__ void timed_wait(const WaShared& sh, uint64_t* bar, uint32_t parity, int slot, int item = -1) {
-  if (sh.prof == nullptr) {
-    mbar_wait(bar, parity);
+  if (!PROF) {
+    mbar_wait_parked(bar, parity);
     return;
   }
-  volatile int* abort_flag = reinterpret_cast<volatile int*>(sh.smem + WA_OFF_BAR + 200);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(sh.smem + WA_OFF_BAR + 184);
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (*abort_flag) break;
@@ -202,29 +215,9 @@ __device__ __forceinline__ void reload_bias(uint8_t* smem, const bf16* bias_dens
   asm volatile("bar.sync 7, 640;" ::: "memory");
 }
 
-// additive shift-mask constants (log2 units) of one unit for a row on side (rh_i, rw_i) of the seam: one per key class
-__device__ __forceinline__ void mask_classes(float (&madd)[4], const StageGeom& g, bool shifted, int win, int nw, int nh,
-                                             bool rh_i, bool rw_i) {
-  const float MASK_L2 = -100.0f * 1.4426950408889634f;
-  madd[0] = madd[1] = madd[2] = madd[3] = 0.f;
-  if (shifted) {
-    const bool use_w = ((win & (nw - 1)) == nw - 1) && g.sw, use_h = (((win / nw) & (nh - 1)) == nh - 1) && g.sh;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool ch = (k >> 1) != 0, cw = (k & 1) != 0;
-      madd[k] = ((use_h && ch != rh_i) || (use_w && cw != rw_i)) ? MASK_L2 : 0.f;
-    }
-  }
-}
-
-// mask constant of 8-column group `grp` of the score tile (remap.cuh key_group_class_377)
-__device__ __forceinline__ float mask_of_group(const float (&madd)[4], int grp) {
-  return grp < 6 ? madd[0] : (grp < 11 ? madd[1] : (grp < 16 ? madd[2] : madd[3]));
-}
-
 // Softmax warp. TILE 0: row slots 32 q + lane of every unit, key columns [40 c, 40 c + 40), q = warp & 3, c = warp >> 2.
-// TILE 1: row slots 128 + lane (replicated in every TMEM lane quarter), key columns [40 q, 40 q + 40), q = warp & 3.
-template <int TILE>
+// TILE 1: row slots 128 + lane (replicated in every TMEM lane quarter), key columns [40 q, 40 q + 40), q = c = warp & 3.
+template <int TILE, bool PROF>
 __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_base, int q, int c, const WaItemCtx& cx) {
   // the pointer must be derived from the __shared__ array itself, otherwise every access below compiles to generic LD/ST
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -233,19 +226,29 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
   const int slot = TILE == 0 ? q * 32 + lane : 128 + lane;  // row slot of this thread
   const int prow = TILE == 0 ? slot : lane;                 // row inside the tile's P operand
   float* sMax = reinterpret_cast<float*>(smem + WA_OFF_M) + (TILE == 0 ? 0 : 2 * 4 * 128);
-  const int mrows = TILE == 0 ? 128 : 32;
+  float* sSum1 = reinterpret_cast<float*>(smem + WA_OFF_SUM1);  // [2][3][32], row tile 1 only
+  constexpr int mrows = TILE == 0 ? 128 : 32;
   const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
   const uint32_t s_addr = tmem_base + lane_addr + (TILE == 0 ? WA_TM_S0 : WA_TM_S1) + c * WA_QCOLS;
   const uint32_t o_base = tmem_base + lane_addr + (TILE == 0 ? WA_TM_O0 : WA_TM_O1);
+  const uint32_t sum_base = tmem_base + lane_addr + WA_TM_SUM;  // row tile 0: [2 slots][4 warps of the row]
   uint8_t* p_base = smem + (TILE == 0 ? WA_OFF_P0 : WA_OFF_P1) + core_off(prow, c * (WA_QCOLS / 8), WA_KEYS / 8);
-  const int p_stride = TILE == 0 ? WA_P0_BYTES : WA_P1_BYTES;
+  constexpr int p_stride = TILE == 0 ? WA_P0_BYTES : WA_P1_BYTES;
   const int tokw = slot_token_377(slot);  // window token of this row, -1 for a pad slot
   const bool valid = tokw >= 0;
   const int brow = valid ? slot : 0;
   const bf16* bias_row = reinterpret_cast<const bf16*>(smem + WA_OFF_BIAS) + brow * WA_BIAS_PITCH + c * WA_QCOLS;
   const float* bmax = reinterpret_cast<const float*>(smem + WA_OFF_BMAX) + brow;
+  // shift mask (video_swin_ori.py:346-358) of a bottom / right border window: key group k of this warp is masked for this
+  // row iff they lie on different sides of the h seam (bit k of mh) or of the w seam (bit k of mw)
   const int row_cls = (slot >= 48) + (slot >= 88) + (slot >= 128);
-  const bool rh_i = row_cls >= 2, rw_i = (row_cls & 1) != 0;  // side of the seam of a bottom / right border window
+  uint32_t mh = 0, mw = 0;
+#pragma unroll
+  for (int k = 0; k < WA_QCOLS / 8; ++k) {
+    const int kc = key_group_class_377(c * (WA_QCOLS / 8) + k);
+    mh |= static_cast<uint32_t>((kc >> 1) != (row_cls >> 1)) << k;
+    mw |= static_cast<uint32_t>((kc & 1) != (row_cls & 1)) << k;
+  }
   const int nw = g.W / g.ww, nh = g.H / g.wh;
   const int lw = 31 - __clz(nw);  // H/7 and W/7 are powers of two on this path (8, 4, 2, 1)
   const int tw = valid ? tokw : 0;
@@ -257,37 +260,38 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
   uint64_t* s_free = sh.s_free + TILE;
   uint64_t* p_full = sh.p_full + 2 * TILE;
   uint64_t* o_full = sh.o_full + 2 * TILE;
-  const bool timing = sh.prof != nullptr && blockIdx.x == 0 && lane == 0;
+  const bool timing = PROF && blockIdx.x == 0 && lane == 0;
+  const float MASK_L2 = -100.0f * 1.4426950408889634f;
 
-  int tok_prev = 0, seg_prev = 0, head_prev = 0, head_loaded = -1;
+  float sum_prev = 0.f;        // tile 1, warp 16: own partial row sum of the previous unit
+  bf16* dst_prev = cx.out;     // output row of the previous unit
 
-  // epilogue of unit jp: normalise by the row sum (column 32 of the output buffer) and scatter through the inverse remap
-  auto store_o = [&](int jp, int seg, int tok, int head) {
-    timed_wait(sh, o_full + (jp & 1), (jp >> 1) & 1, 1, jp);
+  // epilogue of unit jp: 1 / (sum of the four partial row sums), scatter through the inverse remap
+  auto store_o = [&](int jp) {
+    timed_wait<PROF>(sh, o_full + (jp & 1), (jp >> 1) & 1, 1, jp);
     if (!stores) return;
     tcgen05_fence_after();
     const uint32_t o_addr = o_base + (jp & 1) * WA_ON;
-    bf16* dst = cx.out + (static_cast<size_t>(seg) * cx.T + tok) * cx.C + head * 32;
     if (TILE == 0) {
-      uint32_t o8[8];
-      const uint32_t l_u = tmem_ld_32x1(o_addr + 32);
+      uint32_t o8[8], l4[4];
+      tmem_ld_32x4(sum_base + (jp & 1) * 4, l4);
       tmem_ld_32x8(o_addr + c * 8, o8);
       tmem_ld_wait();
       tcgen05_fence_before();
-      const float inv = 1.0f / __uint_as_float(l_u);
+      const float inv = 1.0f / ((__uint_as_float(l4[0]) + __uint_as_float(l4[1])) + (__uint_as_float(l4[2]) + __uint_as_float(l4[3])));
       uint4 o;
       o.x = pack_bf16x2(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv);
       o.y = pack_bf16x2(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv);
       o.z = pack_bf16x2(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv);
       o.w = pack_bf16x2(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv);
-      if (valid) *reinterpret_cast<uint4*>(dst + c * 8) = o;
+      if (valid) *reinterpret_cast<uint4*>(dst_prev + c * 8) = o;
     } else {
       uint32_t o32[32];
-      const uint32_t l_u = tmem_ld_32x1(o_addr + 32);
       tmem_ld_32x32(o_addr, o32);
+      const float* ls = sSum1 + (jp & 1) * 96 + lane;
+      const float inv = 1.0f / ((sum_prev + ls[0]) + (ls[32] + ls[64]));
       tmem_ld_wait();
       tcgen05_fence_before();
-      const float inv = 1.0f / __uint_as_float(l_u);
       if (valid) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -296,30 +300,33 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
           o.y = pack_bf16x2(__uint_as_float(o32[8 * k + 2]) * inv, __uint_as_float(o32[8 * k + 3]) * inv);
           o.z = pack_bf16x2(__uint_as_float(o32[8 * k + 4]) * inv, __uint_as_float(o32[8 * k + 5]) * inv);
           o.w = pack_bf16x2(__uint_as_float(o32[8 * k + 6]) * inv, __uint_as_float(o32[8 * k + 7]) * inv);
-          reinterpret_cast<uint4*>(dst)[k] = o;
+          reinterpret_cast<uint4*>(dst_prev)[k] = o;
         }
       }
     }
   };
 
-  int head = cx.u_lo / cx.n_items, item = cx.u_lo - head * cx.n_items - 1;
+  int head = cx.u_lo / cx.n_items, item = cx.u_lo - head * cx.n_items;
+  int seg = item / cx.nwin, win = item - seg * cx.nwin;
+  int head_loaded = -1;
   for (int j = 0; j < cx.n_my; ++j) {
-    if (++item == cx.n_items) { item = 0; ++head; }
-    const int seg = item / cx.nwin, win = item - seg * cx.nwin;
     if (head != head_loaded) {
       reload_bias(smem, cx.bias_dense, head);
       head_loaded = head;
     }
-    float madd[4];
-    mask_classes(madd, g, cx.shifted, win, nw, nh, rh_i, rw_i);
-    int tok;
+    // per-unit geometry of this row: mask bits of the five key groups, output row
+    const int wy = (win >> lw) & (nh - 1), wx = win & (nw - 1);
+    uint32_t mbits = 0;
+    if (cx.shifted) mbits = ((wy == nh - 1 && g.sh) ? mh : 0u) | ((wx == nw - 1 && g.sw) ? mw : 0u);
+    bf16* dst;
     {
-      int y = ((win >> lw) & (nh - 1)) * 7 + g.sh + row_h, x = (win & (nw - 1)) * 7 + g.sw + row_w;
+      int y = wy * 7 + g.sh + row_h, x = wx * 7 + g.sw + row_w;
       if (y >= g.H) y -= g.H;
       if (x >= g.W) x -= g.W;
-      tok = (row_d * g.H + y) * g.W + x;  // == window_source_token_377(g, hW, wW, tokw)
+      const int tok = (row_d * g.H + y) * g.W + x;  // == window_source_token_377(g, wy, wx, tokw)
+      dst = cx.out + (static_cast<size_t>(seg) * cx.T + tok) * cx.C + head * 32;
     }
-    timed_wait(sh, s_full, j & 1, 0, j);
+    timed_wait<PROF>(sh, s_full, j & 1, 0, j);
     tcgen05_fence_after();
     long long tc0 = timing ? clock64() : 0;
     float s[WA_QCOLS];
@@ -334,7 +341,8 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     __syncwarp();
     if (lane == 0) mbar_arrive(s_free);
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 4] += tc - tc0; tc0 = tc; }  // [4] TMEM load of S
-    // ---- raw-score maximum of the row: own 40 columns, then the four warps of the row through shared memory
+    // ---- raw-score maximum of the row: own 40 columns, then the four warps of the row through shared memory. The
+    // barrier also orders the partial row sums of unit j-1 (written before it) against their readers (store_o below).
     float mx = s[0];
 #pragma unroll
     for (int e = 1; e < WA_QCOLS; ++e) mx = fmaxf(mx, s[e]);
@@ -342,20 +350,23 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
     for (int k = 0; k < 4; ++k) mx = fmaxf(mx, sMax[((j & 1) * 4 + k) * mrows + prow]);
-    const float bound = fmaf(mx, cx.scale_log2e, *bmax);  // >= every t_ij of the row
+    const float nbound = -fmaf(mx, cx.scale_log2e, *bmax);  // -(upper bound of every t_ij of the row)
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 5] += tc - tc0; tc0 = tc; }  // [5] maximum + exchange
     // ---- p = exp2(s * scale*log2e + bias + mask - bound) -> bf16 A-operand tile (buffer j & 1: P v(j-2) has completed,
     // observed at the epilogue of unit j-2); pad columns carry a bias of -inf
     uint8_t* p_row = p_base + (j & 1) * p_stride;
+    float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int cc = 0; cc < WA_QCOLS; cc += 8) {
       const uint4 b4 = *reinterpret_cast<const uint4*>(bias_row + cc);
       const float2 b01 = unpack_bf16x2(b4.x), b23 = unpack_bf16x2(b4.y), b45 = unpack_bf16x2(b4.z), b67 = unpack_bf16x2(b4.w);
       const float bb[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
-      const float cg = mask_of_group(madd, c * (WA_QCOLS / 8) + cc / 8) - bound;
+      const float cg = ((mbits >> (cc / 8)) & 1u) ? nbound + MASK_L2 : nbound;
       float p[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) p[e] = ex2_approx(fmaf(s[cc + e], cx.scale_log2e, bb[e] + cg));
+      l0 += (p[0] + p[1]) + (p[2] + p[3]);
+      l1 += (p[4] + p[5]) + (p[6] + p[7]);
       uint4 u;
       u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
       u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
@@ -365,15 +376,35 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     __syncwarp();
     if (lane == 0) mbar_arrive(p_full + (j & 1));
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 6] += tc - tc0; tc0 = tc; }  // [6] probabilities
-    // ---- epilogue of the previous unit (its P v was issued a whole softmax ago). Program order puts these TMEM reads
-    // before this warp's next arrival on p_full, i.e. before P v(j+1) overwrites the same output buffer.
-    if (j > 0) store_o(j - 1, seg_prev, tok_prev, head_prev);
+    // ---- epilogue of the previous unit (its P v was issued a whole softmax ago; its partial row sums were published
+    // before this unit's barrier). Program order puts these TMEM reads before this warp's next arrival on p_full, i.e.
+    // before P v(j+1) overwrites the same output buffer.
+    if (j > 0) store_o(j - 1);
+    // ---- publish this unit's partial row sum (slot j & 1; its last readers ran before the barrier of unit j... j-1's
+    // epilogue above read slot (j-1) & 1, and slot j & 1 was last read in iteration j-1, before this unit's barrier)
+    if (TILE == 0) {
+      tmem_st_32x1(sum_base + (j & 1) * 4 + c, __float_as_uint(l0 + l1));
+      tmem_st_wait();
+      tcgen05_fence_before();
+    } else {
+      if (q == 0) sum_prev = l0 + l1;
+      else sSum1[((j & 1) * 3 + (q - 1)) * 32 + lane] = l0 + l1;
+    }
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 7] += tc - tc0; tc0 = tc; }  // [7] epilogue
-    tok_prev = tok; seg_prev = seg; head_prev = head;
+    dst_prev = dst;
+    if (++win == cx.nwin) {
+      win = 0;
+      if (++seg * cx.nwin == cx.n_items) { seg = 0; ++head; }
+    }
   }
-  if (cx.n_my > 0) store_o(cx.n_my - 1, seg_prev, tok_prev, head_prev);
+  if (cx.n_my > 0) {
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // partial row sums of the last unit
+    if (TILE == 0) tcgen05_fence_after();
+    store_o(cx.n_my - 1);
+  }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(WA_THREADS, 1)
 window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ out, const bf16* __restrict__ bias_dense,
                         StageGeom g, int n_seg, int C, int n_heads, float scale_log2e, long long* prof) {
@@ -391,7 +422,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
   sh.s_free = sh.s_full + 2;                                    // [2]
   sh.p_full = sh.s_free + 2;                                    // [4]
   sh.o_full = sh.p_full + 4;                                    // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sh.o_full + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sh.o_full + 4);  // byte 160; watchdog flag at byte 184
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwin = windows_per_segment(g);
@@ -404,14 +435,13 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
   const int u_lo = static_cast<int>(n_units * blockIdx.x / gridDim.x);
   const int u_hi = static_cast<int>(n_units * (blockIdx.x + 1) / gridDim.x);
   const int n_my = u_hi - u_lo;
-  if (prof != nullptr && blockIdx.x == 0 && tid == 0) prof[24 * 8 + 2] = clock64();
+  if (PROF && blockIdx.x == 0 && tid == 0) prof[24 * 8 + 2] = clock64();
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled TMA / UMMA tiles assume an aligned window
 
-  // ---- one-time setup: zero the staging and P buffers (pad slots stay zero forever), the ones tile, barriers, TMEM
+  // ---- one-time setup: zero the staging and P buffers (pad slots stay zero forever), barriers, TMEM
   for (int i = tid; i < WA_OFF_BIAS / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < 32) reinterpret_cast<uint4*>(smem + WA_OFF_ONES)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (warp == WA_WARP_MMA0 && lane == 0) {
-    *reinterpret_cast<volatile int*>(smem + WA_OFF_BAR + 200) = 0;  // watchdog abort flag (profiling hook only)
+    *reinterpret_cast<volatile int*>(smem + WA_OFF_BAR + 184) = 0;  // watchdog abort flag (profiling hook only)
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh.qk_full[b], 1);
       mbar_init(&sh.qk_empty[b], 2);  // S0 (warp 21) and S1 (warp 22) both read q / k
@@ -444,44 +474,69 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
     if (lane == 0) {
       const int lw = 31 - __clz(g.W / 7);  // H/7 and W/7 are powers of two on this path (8, 4, 2, 1)
       const int nh_mask = g.H / 7 - 1, nw_mask = g.W / 7 - 1;
-      int head = u_lo / n_items, item = u_lo - head * n_items;
       const uint32_t smem0 = smem_u32(smem);
-      for (int j = 0; j < n_my; ++j) {
+      // unit -> TMA coordinates: channel of the head's q slice, (x, y) of the parts before / behind the seam (only the
+      // part behind the seam can wrap), first frame row of the segment
+      struct Coord { int cq, xa, xb, ya, yb, ds; };
+      int head = u_lo / n_items, item = u_lo - head * n_items;
+      int seg = item / nwin, win = item - seg * nwin;
+      auto coord_next = [&]() {
+        Coord k;
+        k.ya = ((win >> lw) & nh_mask) * 7 + g.sh; k.xa = (win & nw_mask) * 7 + g.sw;
+        k.yb = k.ya + 4; k.xb = k.xa + 4;
+        if (k.yb >= g.H) k.yb -= g.H;
+        if (k.xb >= g.W) k.xb -= g.W;
+        k.cq = head * 32; k.ds = seg * 3;
+        if (++win == nwin) {
+          win = 0;
+          if (++seg * nwin == n_items) { seg = 0; ++head; }
+        }
+        return k;
+      };
+      auto load_qk = [&](int j, const Coord& k) {
         const int buf = j & 1;
-        const int seg = item / nwin, win = item - seg * nwin;
-        int ya = ((win >> lw) & nh_mask) * 7 + g.sh, xa = (win & nw_mask) * 7 + g.sw;
-        int yb = ya + 4, xb = xa + 4;  // the part behind the seam; it is the one that may wrap
-        if (yb >= g.H) yb -= g.H;
-        if (xb >= g.W) xb -= g.W;
-        const int cq = head * 32, ds = seg * 3;
-        const uint32_t sq = smem0 + WA_OFF_STAGE + buf * WA_STAGE_BYTES, sk = sq + WA_Q_BYTES, sv = sk + WA_K_BYTES;
-        timed_wait(sh, &sh.qk_empty[buf], ((j >> 1) & 1) ^ 1, 0, j);
-        mbar_expect_tx(&sh.qk_full[buf], WA_QK_TX_BYTES);
-        tma_load_4d(sk + 0 * 64, &maps.m[0], &sh.qk_full[buf], C + cq, xa, ya, ds);
-        tma_load_4d(sk + 48 * 64, &maps.m[1], &sh.qk_full[buf], C + cq, xb, ya, ds);
-        tma_load_4d(sk + 88 * 64, &maps.m[2], &sh.qk_full[buf], C + cq, xa, yb, ds);
-        tma_load_4d(sk + 128 * 64, &maps.m[3], &sh.qk_full[buf], C + cq, xb, yb, ds);
-        tma_load_4d(sq + 0 * 64, &maps.m[0], &sh.qk_full[buf], cq, xa, ya, ds);
-        tma_load_4d(sq + 48 * 64, &maps.m[1], &sh.qk_full[buf], cq, xb, ya, ds);
-        tma_load_4d(sq + 88 * 64, &maps.m[2], &sh.qk_full[buf], cq, xa, yb, ds);
+        const uint32_t sq = smem0 + WA_OFF_STAGE + buf * WA_STAGE_BYTES, sk = sq + WA_Q_BYTES;
+        uint64_t* bar = &sh.qk_full[buf];
+        timed_wait<PROF>(sh, &sh.qk_empty[buf], ((j >> 1) & 1) ^ 1, 0, j);
+        mbar_expect_tx(bar, WA_QK_TX_BYTES);
+        tma_load_4d(sk + 0 * 64, &maps.m[0], bar, C + k.cq, k.xa, k.ya, k.ds);
+        tma_load_4d(sk + 48 * 64, &maps.m[1], bar, C + k.cq, k.xb, k.ya, k.ds);
+        tma_load_4d(sk + 88 * 64, &maps.m[2], bar, C + k.cq, k.xa, k.yb, k.ds);
+        tma_load_4d(sk + 128 * 64, &maps.m[3], bar, C + k.cq, k.xb, k.yb, k.ds);
+        tma_load_4d(sq + 0 * 64, &maps.m[0], bar, k.cq, k.xa, k.ya, k.ds);
+        tma_load_4d(sq + 48 * 64, &maps.m[1], bar, k.cq, k.xb, k.ya, k.ds);
+        tma_load_4d(sq + 88 * 64, &maps.m[2], bar, k.cq, k.xa, k.yb, k.ds);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tma_load_4d(sq + (128 + 32 * k) * 64, &maps.m[3], &sh.qk_full[buf], cq, xb, yb, ds);
-        timed_wait(sh, &sh.v_empty[buf], ((j >> 1) & 1) ^ 1, 3, j);
-        mbar_expect_tx(&sh.v_full[buf], WA_V_TX_BYTES);
-        tma_load_4d(sv + 0 * 64, &maps.m[0], &sh.v_full[buf], 2 * C + cq, xa, ya, ds);
-        tma_load_4d(sv + 48 * 64, &maps.m[1], &sh.v_full[buf], 2 * C + cq, xb, ya, ds);
-        tma_load_4d(sv + 88 * 64, &maps.m[2], &sh.v_full[buf], 2 * C + cq, xa, yb, ds);
-        tma_load_4d(sv + 128 * 64, &maps.m[3], &sh.v_full[buf], 2 * C + cq, xb, yb, ds);
-        if (++item == n_items) { item = 0; ++head; }
+        for (int r = 0; r < 4; ++r) tma_load_4d(sq + (128 + 32 * r) * 64, &maps.m[3], bar, k.cq, k.xb, k.yb, k.ds);
+      };
+      // q / k of unit j+1 are requested BEFORE v of unit j: their buffer is free as soon as S(j-1) has been issued, a whole
+      // unit earlier than the v buffer (P v(j-2))
+      Coord cur = coord_next();
+      load_qk(0, cur);
+      for (int j = 0; j < n_my; ++j) {
+        Coord nxt = cur;
+        if (j + 1 < n_my) {
+          nxt = coord_next();
+          load_qk(j + 1, nxt);
+        }
+        const int buf = j & 1;
+        const uint32_t sv = smem0 + WA_OFF_STAGE + buf * WA_STAGE_BYTES + WA_Q_BYTES + WA_K_BYTES;
+        uint64_t* bar = &sh.v_full[buf];
+        timed_wait<PROF>(sh, &sh.v_empty[buf], ((j >> 1) & 1) ^ 1, 3, j);
+        mbar_expect_tx(bar, WA_V_TX_BYTES);
+        tma_load_4d(sv + 0 * 64, &maps.m[0], bar, 2 * C + cur.cq, cur.xa, cur.ya, cur.ds);
+        tma_load_4d(sv + 48 * 64, &maps.m[1], bar, 2 * C + cur.cq, cur.xb, cur.ya, cur.ds);
+        tma_load_4d(sv + 88 * 64, &maps.m[2], bar, 2 * C + cur.cq, cur.xa, cur.yb, cur.ds);
+        tma_load_4d(sv + 128 * 64, &maps.m[3], bar, 2 * C + cur.cq, cur.xb, cur.yb, cur.ds);
+        cur = nxt;
       }
     }
   } else if (warp == WA_WARP_MMA0 || warp == WA_WARP_MMA1) {
     // ===================================================================== MMA issuers: warp 21 -> row tile 0, 22 -> tile 1
     if (lane == 0 && n_my > 0) {
       const int tile = warp == WA_WARP_MMA1;
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_KEYS);        // A, B K-major
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_KEYS);          // A, B K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);  // B (= v) MN-major
-      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16);             // B = ones, K-major
       uint64_t* s_full = sh.s_full + tile;
       uint64_t* s_free = sh.s_free + tile;
       uint64_t* p_full = sh.p_full + 2 * tile;
@@ -490,7 +545,6 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
       // Descriptors of one operand differ only in their start-address field (bits 0..13, in 16-byte units), so every
       // further MMA of a sequence costs one 64-bit add instead of a fresh encode.
       const uint32_t smem0 = smem_u32(smem);
-      const uint64_t d_ones = umma_desc_nosw(smem0 + WA_OFF_ONES, 128, 256);
       auto issue_s = [&](int j) {
         const uint32_t b = smem0 + WA_OFF_STAGE + (j & 1) * WA_STAGE_BYTES;
         const uint64_t dq = umma_desc_sw64(b + tile * (128 * 64)), dk = umma_desc_sw64(b + WA_Q_BYTES);
@@ -499,18 +553,18 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
         umma_commit(s_full);
         umma_commit(&sh.qk_empty[j & 1]);
       };
-      timed_wait(sh, &sh.qk_full[0], 0, 1, 0);
+      timed_wait<PROF>(sh, &sh.qk_full[0], 0, 1, 0);
       tcgen05_fence_after();
       issue_s(0);
       for (int j = 0; j < n_my; ++j) {
         if (j + 1 < n_my) {
-          timed_wait(sh, s_free, j & 1, 0, j);  // every softmax warp of this row tile has S(j) in registers
-          timed_wait(sh, &sh.qk_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 1, j);
+          timed_wait<PROF>(sh, s_free, j & 1, 0, j);  // every softmax warp of this row tile has S(j) in registers
+          timed_wait<PROF>(sh, &sh.qk_full[(j + 1) & 1], ((j + 1) >> 1) & 1, 1, j);
           tcgen05_fence_after();
           issue_s(j + 1);
         }
-        timed_wait(sh, p_full + (j & 1), (j >> 1) & 1, 2, j);  // P(j) in smem, output buffer j & 1 drained (unit j-2)
-        timed_wait(sh, &sh.v_full[j & 1], (j >> 1) & 1, 3, j);
+        timed_wait<PROF>(sh, p_full + (j & 1), (j >> 1) & 1, 2, j);  // P(j) in smem, output buffer j & 1 drained (unit j-2)
+        timed_wait<PROF>(sh, &sh.v_full[j & 1], (j >> 1) & 1, 3, j);
         tcgen05_fence_after();
         const uint64_t dv = umma_desc_sw64(smem0 + WA_OFF_STAGE + (j & 1) * WA_STAGE_BYTES + WA_Q_BYTES + WA_K_BYTES);
         const uint64_t dp = umma_desc_nosw(smem0 + (tile ? WA_OFF_P1 + (j & 1) * WA_P1_BYTES : WA_OFF_P0 + (j & 1) * WA_P0_BYTES),
@@ -519,10 +573,8 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
 #pragma unroll
         for (int kk = 0; kk < WA_KEYS / 16; ++kk)  // 16 keys per step: 2 cores of P (256 B), 2 row groups of v (1024 B)
           umma_bf16_ss(tm_oj, dp + ((kk * 256) >> 4), dv + ((kk * 1024) >> 4), idesc_o, kk);
-        umma_commit(&sh.v_empty[j & 1]);
-#pragma unroll
-        for (int kk = 0; kk < WA_KEYS / 16; ++kk) umma_bf16_ss(tm_oj + 32, dp + ((kk * 256) >> 4), d_ones, idesc_l, kk);
         umma_commit(o_full + (j & 1));
+        umma_commit(&sh.v_empty[j & 1]);
       }
     }
   } else if (warp < 20) {
@@ -530,8 +582,8 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
     WaItemCtx cx;
     cx.bias_dense = bias_dense; cx.out = out; cx.g = g; cx.n_items = n_items; cx.nwin = nwin; cx.T = T; cx.C = C;
     cx.u_lo = u_lo; cx.n_my = n_my; cx.scale_log2e = scale_log2e; cx.shifted = shifted;
-    if (warp < 16) softmax_warp<0>(sh, tmem_base, warp & 3, warp >> 2, cx);
-    else softmax_warp<1>(sh, tmem_base, warp & 3, warp & 3, cx);
+    if (warp < 16) softmax_warp<0, PROF>(sh, tmem_base, warp & 3, warp >> 2, cx);
+    else softmax_warp<1, PROF>(sh, tmem_base, warp & 3, warp & 3, cx);
   }
 
   tcgen05_fence_before();
@@ -540,7 +592,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, WA_TM_COLS);
   }
-  if (prof != nullptr && blockIdx.x == 0 && tid == 0) {
+  if (PROF && blockIdx.x == 0 && tid == 0) {
     prof[24 * 8] = n_my;
     prof[24 * 8 + 1] = clock64() - prof[24 * 8 + 2];
   }
@@ -645,7 +697,9 @@ extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void
   LRCE_REQUIRE(n_heads > 0 && C == n_heads * 32, "lrce_window_attention_bf16: head_dim must be 32 (C=%d heads=%d)", C, n_heads);
   static thread_local bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(window_attention_kernel): %s", cudaGetErrorString(e));
       return LRCE_ECUDA;
@@ -659,9 +713,14 @@ extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void
   int grid = sm_count();  // one persistent CTA per SM (it owns all 512 TMEM columns)
   if (grid > n_units) grid = static_cast<int>(n_units);
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
-  window_attention_kernel<<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-      *maps, reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e,
-      g_attn_prof);
+  if (g_attn_prof != nullptr)  // profiling hook armed: instrumented instantiation
+    window_attention_kernel<true><<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *maps, reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e,
+        g_attn_prof);
+  else
+    window_attention_kernel<false><<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *maps, reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e,
+        nullptr);
   return check_launch("window_attention_kernel");
 }
 

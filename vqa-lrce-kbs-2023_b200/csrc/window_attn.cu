@@ -355,23 +355,28 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     // ---- p = exp2(s * scale*log2e + bias + mask - bound) -> bf16 A-operand tile (buffer j & 1: P v(j-2) has completed,
     // observed at the epilogue of unit j-2); pad columns carry a bias of -inf
     uint8_t* p_row = p_base + (j & 1) * p_stride;
-    float l0 = 0.f, l1 = 0.f;
+    float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
+    const float2 sc2 = make_float2(cx.scale_log2e, cx.scale_log2e);
 #pragma unroll
     for (int cc = 0; cc < WA_QCOLS; cc += 8) {
       const uint4 b4 = *reinterpret_cast<const uint4*>(bias_row + cc);
-      const float2 b01 = unpack_bf16x2(b4.x), b23 = unpack_bf16x2(b4.y), b45 = unpack_bf16x2(b4.z), b67 = unpack_bf16x2(b4.w);
-      const float bb[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
       const float cg = ((mbits >> (cc / 8)) & 1u) ? nbound + MASK_L2 : nbound;
-      float p[8];
+      const float2 cg2 = make_float2(cg, cg);
+      const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+      float2 p[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) p[e] = ex2_approx(fmaf(s[cc + e], cx.scale_log2e, bb[e] + cg));
-      l0 += (p[0] + p[1]) + (p[2] + p[3]);
-      l1 += (p[4] + p[5]) + (p[6] + p[7]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = ffma2(make_float2(s[cc + 2 * e], s[cc + 2 * e + 1]), sc2, fadd2(bf16x2_to_f32x2(bw[e]), cg2));
+        p[e] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+      }
+      l01 = fadd2(l01, fadd2(p[0], p[1]));
+      l23 = fadd2(l23, fadd2(p[2], p[3]));
       uint4 u;
-      u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-      u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+      u.x = pack_bf16x2(p[0].x, p[0].y); u.y = pack_bf16x2(p[1].x, p[1].y);
+      u.z = pack_bf16x2(p[2].x, p[2].y); u.w = pack_bf16x2(p[3].x, p[3].y);
       *reinterpret_cast<uint4*>(p_row + (cc / 8) * 128) = u;
     }
+    const float l0 = l01.x + l01.y, l1 = l23.x + l23.y;
     fence_proxy_async_smem();  // P writes -> visible to the tensor core
     __syncwarp();
     if (lane == 0) mbar_arrive(p_full + (j & 1));

@@ -237,7 +237,11 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
   const int tokw = slot_token_377(slot);  // window token of this row, -1 for a pad slot
   const bool valid = tokw >= 0;
   const int brow = valid ? slot : 0;
-  const bf16* bias_row = reinterpret_cast<const bf16*>(smem + WA_OFF_BIAS) + brow * WA_BIAS_PITCH + c * WA_QCOLS;
+  // bias rows are stored with their 16-byte chunks XOR-swizzled by ((row >> 1) & 3) (lrce_window_bias_pack): the eight
+  // lanes of an LDS.128 phase read the same logical chunk of eight consecutive 320-byte rows, which would otherwise be a
+  // 4-way bank conflict
+  const bf16* bias_row = reinterpret_cast<const bf16*>(smem + WA_OFF_BIAS) + brow * WA_BIAS_PITCH;
+  const int bias_sw = (brow >> 1) & 3;
   const float* bmax = reinterpret_cast<const float*>(smem + WA_OFF_BMAX) + brow;
   // shift mask (video_swin_ori.py:346-358) of a bottom / right border window: key group k of this warp is masked for this
   // row iff they lie on different sides of the h seam (bit k of mh) or of the w seam (bit k of mw)
@@ -359,7 +363,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     const float2 sc2 = make_float2(cx.scale_log2e, cx.scale_log2e);
 #pragma unroll
     for (int cc = 0; cc < WA_QCOLS; cc += 8) {
-      const uint4 b4 = *reinterpret_cast<const uint4*>(bias_row + cc);
+      const uint4 b4 = *reinterpret_cast<const uint4*>(bias_row + ((c * (WA_QCOLS / 8) + cc / 8) ^ bias_sw) * 8);
       const float cg = ((mbits >> (cc / 8)) & 1u) ? nbound + MASK_L2 : nbound;
       const float2 cg2 = make_float2(cg, cg);
       const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -603,7 +607,8 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
   }
 }
 
-// dense[h][slot_i][slot_j] = table[rel_index(tok_i, tok_j)][h] * log2(e) for rows 0..154 (pad key columns -inf, pad rows 0);
+// dense[h][slot_i][slot_j] = table[rel_index(tok_i, tok_j)][h] * log2(e) for rows 0..154 (pad key columns -inf, pad rows 0),
+// the 16-byte chunks of row i stored at chunk index (j / 8) ^ ((i >> 1) & 3) (bank-conflict-free row-per-lane reads);
 // rows 155, 156 of every head hold float bmax[160] = max_j dense[h][slot_i][.] (0 for pad rows)
 __global__ void build_dense_bias_kernel(const float* __restrict__ table, bf16* __restrict__ dense, StageGeom g,
                                         int n_heads) {
@@ -626,7 +631,7 @@ __global__ void build_dense_bias_kernel(const float* __restrict__ table, bf16* _
       }
       mx = fmaxf(mx, __bfloat162float(v));
     }
-    if (si < WA_BIAS_ROWS) head[si * WA_BIAS_PITCH + sj] = v;
+    if (si < WA_BIAS_ROWS) head[si * WA_BIAS_PITCH + (((sj >> 3) ^ ((si >> 1) & 3)) << 3) + (sj & 7)] = v;
   }
   bmax[si] = mx;
 }

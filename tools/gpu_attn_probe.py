@@ -3,7 +3,10 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import lrce_b200
-from lrce_b200 import ops
+from lrce_b200 import ops, _lib as _l
+if os.environ.get('ATTN_LIB'):
+    _l.LIB_PATH = os.environ['ATTN_LIB']  # A/B variants of the library (tools only)
+    print('library', _l.LIB_PATH)
 
 n_seg = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 stages = [("s1", 56, 128, 4), ("s2", 28, 256, 8), ("s3", 14, 512, 16), ("s4", 7, 1024, 32)]

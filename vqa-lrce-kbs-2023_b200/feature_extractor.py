@@ -270,7 +270,12 @@ class VideoExtractor(nn.Module):
 
 class TextExtractor(nn.Module):
     """lrce.feature_extractor.text.TextExtractor (text.py:5-17): HF BertModel, unchanged PyTorch.
-    Runs under bf16 autocast regardless of the ambient autocast dtype."""
+    Runs under bf16 autocast regardless of the ambient autocast dtype.
+
+    BERT-base on one batch of questions is ~400 short library kernels: launch-bound (5 ms of host time for < 1 ms of
+    device work). In inference (no grad) the forward is therefore captured once per input shape into a CUDA graph and
+    replayed; the graph reads the live parameters, so weight updates / `load_state_dict` need no re-capture. Set
+    LRCE_B200_BERT_GRAPH=0 to run the module eagerly."""
 
     def __init__(self, pretrained=True):
         super().__init__()
@@ -280,8 +285,70 @@ class TextExtractor(nn.Module):
             self.bert = transformers.BertModel.from_pretrained("bert-base-uncased")
         else:
             self.bert = transformers.BertModel(transformers.BertConfig())
+        self._graphs = {}  # (shape, device, param identity) -> (graph, static inputs, static output); never pickled
+        self._graph_failed = False
 
-    def forward(self, input_ids, attention_mask, token_type_ids):
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_graphs"] = {}
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        graphs, self._graphs = self._graphs, {}
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            new.__dict__ = copy.deepcopy(self.__dict__, memo)
+        finally:
+            self._graphs = graphs
+        return new
+
+    def _eager(self, input_ids, attention_mask, token_type_ids):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return self.bert(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids,
                              output_hidden_states=False).last_hidden_state
+
+    def _param_key(self):
+        p = next(self.bert.parameters())
+        return (p.data_ptr(), p.dtype, self.bert.training)
+
+    def forward(self, input_ids, attention_mask, token_type_ids):
+        use_graph = (input_ids.is_cuda and not torch.is_grad_enabled() and not self.bert.training
+                     and not self._graph_failed and os.environ.get("LRCE_B200_BERT_GRAPH", "1") != "0"
+                     and not torch.cuda.is_current_stream_capturing())
+        if not use_graph:
+            return self._eager(input_ids, attention_mask, token_type_ids)
+        key = (tuple(input_ids.shape), input_ids.dtype, attention_mask.dtype, token_type_ids.dtype, input_ids.device,
+               self._param_key())
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 8:  # shapes are few in practice (one per dataset config); drop the oldest
+                self._graphs.pop(next(iter(self._graphs)))
+            static_in = [input_ids.clone(), attention_mask.clone(), token_type_ids.clone()]
+            cur = torch.cuda.current_stream(input_ids.device)
+            warm = torch.cuda.Stream(device=input_ids.device)
+            warm.wait_stream(cur)
+            with torch.cuda.stream(warm):  # library warm-up (lazy handles, autotune) outside the capture
+                for _ in range(2):
+                    self._eager(*static_in)
+            cur.wait_stream(warm)
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    static_out = self._eager(*static_in)
+            except Exception as e:  # a library op that cannot be captured: stay eager from now on (still the same math)
+                self._graph_failed = True
+                import warnings
+
+                warnings.warn(f"lrce_b200: BERT CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
+                torch.cuda.synchronize(input_ids.device)
+                return self._eager(input_ids, attention_mask, token_type_ids)
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        for dst, src in zip(static_in, (input_ids, attention_mask, token_type_ids)):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()  # on the caller's current stream (the E2E module's side stream)
+        return static_out.clone()  # the static output is rewritten by the next replay

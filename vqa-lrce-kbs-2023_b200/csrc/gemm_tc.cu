@@ -64,16 +64,22 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + GEMM_EPI_WARPS * SLAB_BYTES + RN_BYTES + 256 /*barriers*/;
 };
 
-// erf-GELU (nn.GELU default, video_swin_ori.py:42) as x * sigmoid(2u), u = x (a + b x^2 + c x^4) fitted to the erf form:
-// max |error| 2.6e-5 over all x (well below the bf16 rounding of the result), 7 FMA-pipe ops + 2 MUFU.
-__device__ __forceinline__ float gelu_sig(float x) {
-  const float x2 = fminf(x * x, 64.0f);
-  float p = fmaf(0.001014263f, x2, -0.106775716f);
-  p = fmaf(p, x2, -2.3011212f);
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return x * r;
+// erf-GELU (nn.GELU default, video_swin_ori.py:42) as 0.5 x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form
+// (0.5 (1 + tanh u) == sigmoid(2u) ~= Phi(x)): max |error| 2.5e-5 over all x before the approximate tanh, whose 2^-11
+// relative error stays below half a bf16 ulp of the result. Two values at a time: 6 packed FMA-pipe ops + ONE MUFU per
+// value — the fc1 epilogues of stages 1-2 are bound by the 16 MUFU / clk / SM, so the sigmoid form (ex2 + rcp) cost twice.
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  float2 x2 = fmul2(x, x);
+  x2.x = fminf(x2.x, 64.0f);
+  x2.y = fminf(x2.y, 64.0f);
+  float2 p = ffma2(x2, make_float2(-0.00035151677f, -0.00035151677f), make_float2(0.03700564325f, 0.03700564325f));
+  p = ffma2(p, x2, make_float2(0.79750783595f, 0.79750783595f));
+  const float2 u = fmul2(p, x);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, t, hx);
 }
 
 // (mean, M2) of 32 values
@@ -136,13 +142,15 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&acc)[32], int c
   if (LNIN) {
     const float4* c4 = reinterpret_cast<const float4*>(p.in_colsum + col0);
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+    const float2 rx = make_float2(rn.x, rn.x), ry = make_float2(rn.y, rn.y);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 c = __ldg(c4 + i), b = __ldg(b4 + i);
-      v[4 * i + 0] = fmaf(rn.x, __uint_as_float(acc[4 * i + 0]), fmaf(rn.y, c.x, b.x));
-      v[4 * i + 1] = fmaf(rn.x, __uint_as_float(acc[4 * i + 1]), fmaf(rn.y, c.y, b.y));
-      v[4 * i + 2] = fmaf(rn.x, __uint_as_float(acc[4 * i + 2]), fmaf(rn.y, c.z, b.z));
-      v[4 * i + 3] = fmaf(rn.x, __uint_as_float(acc[4 * i + 3]), fmaf(rn.y, c.w, b.w));
+      const float2 lo = ffma2(rx, make_float2(__uint_as_float(acc[4 * i + 0]), __uint_as_float(acc[4 * i + 1])),
+                              ffma2(ry, make_float2(c.x, c.y), make_float2(b.x, b.y)));
+      const float2 hi = ffma2(rx, make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])),
+                              ffma2(ry, make_float2(c.z, c.w), make_float2(b.z, b.w)));
+      v[4 * i + 0] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
     }
   } else {
 #pragma unroll
@@ -161,7 +169,10 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&acc)[32], int c
   }
   if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_sig(v[i]);
+    for (int i = 0; i < 32; i += 2) {
+      const float2 g = gelu_tanh2(make_float2(v[i], v[i + 1]));
+      v[i] = g.x; v[i + 1] = g.y;
+    }
   }
   if (EPI == EPI_BIAS_RESIDUAL) {
 #pragma unroll

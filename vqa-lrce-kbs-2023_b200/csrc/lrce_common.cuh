@@ -261,6 +261,16 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "mul.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 // bf16x2 word -> two fp32 (element 0 in the low half): one shift, one mask
 __device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));

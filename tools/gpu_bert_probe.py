@@ -35,3 +35,23 @@ with torch.no_grad():
     model.text_extractor.forward = orig
     swin = timeit(lambda: model.extract_video_features(inputs[0]))
 print(f"E2E forward {full:.2f} ms | with cached text features {nobert:.2f} ms | BERT alone {bert:.2f} ms | Swin alone {swin:.2f} ms")
+
+# ---- the same question for the Swin path: eager launches (ctypes -> liblrce_b200) vs one CUDA graph replay
+with torch.no_grad():
+    static = inputs[0].clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            model.extract_video_features(static)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out_static = model.extract_video_features(static)
+    ref = model.extract_video_features(static)
+    g.replay()
+    torch.cuda.synchronize()
+    print("graph == eager:", torch.equal(ref, out_static))
+    t_graph = timeit(lambda: g.replay())
+    t_eager = timeit(lambda: model.extract_video_features(static))
+print(f"Swin eager {t_eager:.2f} ms | Swin as one CUDA graph {t_graph:.2f} ms")

@@ -82,16 +82,32 @@ __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
   return ffma2(hx, t, hx);
 }
 
-// (mean, M2) of 32 values
+// (mean, M2) of 32 values: four independent packed accumulators (a serial chain of 32 dependent adds costs ~130 cycles of
+// latency per piece in an epilogue that is latency-bound on the short-K shapes)
 __device__ __forceinline__ float2 stats32(const float (&v)[32]) {
-  float s = 0.f;
+  float2 s0 = make_float2(v[0], v[1]), s1 = make_float2(v[2], v[3]), s2 = make_float2(v[4], v[5]), s3 = make_float2(v[6], v[7]);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) s += v[i];
-  const float mean = s * (1.0f / 32);
-  float m2 = 0.f;
+  for (int i = 8; i < 32; i += 8) {
+    s0 = fadd2(s0, make_float2(v[i + 0], v[i + 1]));
+    s1 = fadd2(s1, make_float2(v[i + 2], v[i + 3]));
+    s2 = fadd2(s2, make_float2(v[i + 4], v[i + 5]));
+    s3 = fadd2(s3, make_float2(v[i + 6], v[i + 7]));
+  }
+  s0 = fadd2(fadd2(s0, s1), fadd2(s2, s3));
+  const float mean = (s0.x + s0.y) * (1.0f / 32);
+  const float2 nm = make_float2(-mean, -mean);
+  float2 m0 = make_float2(0.f, 0.f), m1 = m0, m2 = m0, m3 = m0;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; m2 = fmaf(d, d, m2); }
-  return make_float2(mean, m2);
+  for (int i = 0; i < 32; i += 8) {
+    const float2 d0 = fadd2(make_float2(v[i + 0], v[i + 1]), nm), d1 = fadd2(make_float2(v[i + 2], v[i + 3]), nm);
+    const float2 d2 = fadd2(make_float2(v[i + 4], v[i + 5]), nm), d3 = fadd2(make_float2(v[i + 6], v[i + 7]), nm);
+    m0 = ffma2(d0, d0, m0);
+    m1 = ffma2(d1, d1, m1);
+    m2 = ffma2(d2, d2, m2);
+    m3 = ffma2(d3, d3, m3);
+  }
+  m0 = fadd2(fadd2(m0, m1), fadd2(m2, m3));
+  return make_float2(mean, m0.x + m0.y);
 }
 // Chan's combination of two equally sized groups of n values each
 __device__ __forceinline__ float2 stats_merge(float2 a, float2 b, float n) {
@@ -160,10 +176,9 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&acc)[32], int c
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b = __ldg(b4 + i);
-        v[4 * i + 0] += b.x;
-        v[4 * i + 1] += b.y;
-        v[4 * i + 2] += b.z;
-        v[4 * i + 3] += b.w;
+        const float2 lo = fadd2(make_float2(v[4 * i + 0], v[4 * i + 1]), make_float2(b.x, b.y));
+        const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+        v[4 * i + 0] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
       }
     }
   }
@@ -177,11 +192,12 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&acc)[32], int c
   if (EPI == EPI_BIAS_RESIDUAL) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float2 f;
-      f = unpack_bf16x2(res[i].x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-      f = unpack_bf16x2(res[i].y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-      f = unpack_bf16x2(res[i].z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-      f = unpack_bf16x2(res[i].w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      const uint32_t w[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = fadd2(make_float2(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]), bf16x2_to_f32x2(w[k]));
+        v[8 * i + 2 * k] = f.x; v[8 * i + 2 * k + 1] = f.y;
+      }
     }
   }
 }

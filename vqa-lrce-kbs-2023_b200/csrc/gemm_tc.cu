@@ -494,6 +494,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row)[i];
         }
+        if (EPI == EPI_BIAS_RESIDUAL) {
+          // The residual stream was last touched several kernels ago: its rows come from HBM (~1.5 us under load), which
+          // a one-piece-ahead register prefetch cannot cover. Pull this thread's slice of the NEXT tile into L2 now, a whole
+          // tile ahead of its use.
+          const int tn = t + n_units;
+          if (tn < n_tiles) {
+            const int rown = (tn / n_tiles_n) * (GEMM_BM * CG) + row_off + row_in_tile;
+            if (rown < p.M) {
+              const bf16* nxt = p.residual + static_cast<size_t>(rown) * p.ldr + (tn % n_tiles_n) * BN + part * WCOLS;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            }
+          }
+        }
         if (LNIN) {
           mbar_wait(&bar_rnfull[as], aphase);
           rn = s_rn[as * GEMM_BM + row_in_tile];

@@ -3,6 +3,9 @@ import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import lrce_b200
+from lrce_b200 import _lib as _l
+if os.environ.get('ATTN_LIB'):
+    _l.LIB_PATH = os.environ['ATTN_LIB']  # A/B variants of the library (tools only)
 from lrce_b200 import ops
 
 torch.manual_seed(0)

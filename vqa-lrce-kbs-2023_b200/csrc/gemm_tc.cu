@@ -318,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m0 = (t / n_tiles_n) * (GEMM_BM * CG) + row_off;
         const int n0 = (t % n_tiles_n) * BN;
         for (int kb = 0; kb < n_kb; ++kb) {
-          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_wait_parked(&bar_empty[stage], phase ^ 1);
           if (CG == 2) {
             // both CTAs' bytes are credited to the leader's barrier, which alone expects them
             if (leader) mbar_expect_tx(&bar_full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
@@ -343,11 +343,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = unit; t < n_tiles; t += n_units, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&bar_tempty[as], aphase ^ 1);
+        mbar_wait_parked(&bar_tempty[as], aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < n_kb; ++kb) {
-          mbar_wait(&bar_full[stage], phase);
+          mbar_wait_parked(&bar_full[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
@@ -387,14 +387,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         while (t < n_tiles) {
           int tn = t + n_units;
           if (tn < n_tiles) stats_fetch<4, 4>(tb, p.in_stats, p.M, (tn / n_tiles_n) * (GEMM_BM * CG) + row_off, lane, 0);
-          mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+          mbar_wait_parked(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
           stats_reduce<4, 4>(ta, s_rn + (it & 1) * GEMM_BM, lane, 0, cw, p.K, p.in_eps);
           publish(it);
           t = tn; ++it;
           if (t >= n_tiles) break;
           tn = t + n_units;
           if (tn < n_tiles) stats_fetch<4, 4>(ta, p.in_stats, p.M, (tn / n_tiles_n) * (GEMM_BM * CG) + row_off, lane, 0);
-          mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+          mbar_wait_parked(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
           stats_reduce<4, 4>(tb, s_rn + (it & 1) * GEMM_BM, lane, 0, cw, p.K, p.in_eps);
           publish(it);
           t = tn; ++it;
@@ -407,10 +407,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (n_chunks == 8) {
             float2 ta[4][8];
             stats_fetch<8, 4>(ta, p.in_stats, p.M, m0, lane, 0);
-            mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+            mbar_wait_parked(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
             stats_reduce<8, 4>(ta, dst, lane, 0, cw, p.K, p.in_eps);
           } else {  // 16 chunks (host-checked): two rows at a time
-            mbar_wait(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
+            mbar_wait_parked(&bar_rnempty[it & 1], ((it >> 1) & 1) ^ 1);
 #pragma unroll 1
             for (int i0 = 0; i0 < 4; i0 += 2) {
               float2 ta[2][16];
@@ -437,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + part * WCOLS;
       if constexpr (EPI == EPI_BIAS_LN) {
         static_assert(BN == 128 || EPI != EPI_BIAS_LN, "the LayerNorm epilogue normalises over one 128-wide tile");
-        mbar_wait(&bar_tfull[as], aphase);
+        mbar_wait_parked(&bar_tfull[as], aphase);
         tcgen05_fence_after();
         // full-row LayerNorm: BN == N == 128, this thread holds 32 of the row's 128 features
         float v[32];
@@ -508,12 +508,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (LNIN) {
-          mbar_wait(&bar_rnfull[as], aphase);
+          mbar_wait_parked(&bar_rnfull[as], aphase);
           rn = s_rn[as * GEMM_BM + row_in_tile];
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_rnempty[as]);
         }
-        mbar_wait(&bar_tfull[as], aphase);
+        mbar_wait_parked(&bar_tfull[as], aphase);
         tcgen05_fence_after();
         float2 st_carry = make_float2(0.f, 0.f);
 #pragma unroll
@@ -570,7 +570,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else if constexpr (sizeof(OutT) == 4) {
-        mbar_wait(&bar_tfull[as], aphase);
+        mbar_wait_parked(&bar_tfull[as], aphase);
         tcgen05_fence_after();
 #pragma unroll 1
         for (int c = 0; c < WCOLS; c += 32) {

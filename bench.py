@@ -41,6 +41,9 @@ GFLOP_PER_CLIP = 303.96  # Swin-B 3 x 96.354 + canonical encode
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+GEMM_DRAM_BYTES_PER_STEP = 17607.3e6 + 12948.1e6  # gemm_tc_kernel family, one batch-32 forward (ncu launch list v3)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -326,7 +329,13 @@ def run_b200_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all Linear layers)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": f"{peaks['source']} bf16_tflops_sustained", "traffic": None,
+                         "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+                         # DRAM bytes (read + write) per launch, mean over the 103 GEMM launches of one forward, from the
+                         # committed ncu launch list (profiles/r01_launches_v3_summary.md: 17.61 GB read + 12.95 GB written)
+                         "traffic": GEMM_DRAM_BYTES_PER_STEP / 103.0 if args.config == "msvd-qa-oe" and B == 32 else None,
+                         "traffic_note": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                         "profiles/r01_launches_v3_summary.md",
+                         "algorithmic_bytes_per_launch": g.get("bytes", 0.0) / max(g["launches"], 1),
                          "launches_per_step": g["launches"] / args.steps, "share_of_step": g["ms"] / ms,
                          "whole_forward_tflops": clips_per_s / world * GFLOP_PER_CLIP / 1e3,
                          "whole_forward_frac": clips_per_s / world * GFLOP_PER_CLIP / 1e3 / peak},
@@ -338,7 +347,8 @@ def run_b200_arm(args):
                 "wmsa_block_frac_of_sustained_peak": blk_flops / blk_ms / 1e9 / peak if blk_ms else 0.0,
                 "wmsa_block_frac_of_burst_peak": blk_flops / blk_ms / 1e9 / burst if blk_ms else 0.0,
                 "wmsa_block_ms_per_step": blk_ms / args.steps,
-                "note": "core = QK^T + PV (4*147^2*32 FLOP per window-head), softmax-bound; block = qkv GEMM + core + proj GEMM"},
+                "note": "core = QK^T + PV (4*147^2*32 FLOP per window-head), bound by the softmax warps' per-unit latency chain; "
+                        "block = qkv GEMM + core + proj GEMM"},
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -106,3 +106,47 @@ def test_training_step_matches_inference_path_and_has_grads():
     assert sum(p.grad.abs().sum().item() for p in enc) > 0
     assert all(p.grad is None for p in m.video_extractor.parameters())
     assert all(p.grad is None for p in m.text_extractor.parameters())
+
+
+def test_text_extractor_graph_replay_equals_eager(msvd, monkeypatch):
+    """The CUDA-graph replay of BERT (inference) must return what the eager module returns, for fresh inputs of the captured
+    shape, for a second shape, and after an in-place weight update (the graph reads the live parameters)."""
+    te = msvd.text_extractor
+    _, ids, mask, types = W.make_inputs(2, 3, 32, seed=5)
+    ids, mask, types = ids.cuda(), mask.cuda(), types.cuda()
+    with torch.no_grad():
+        a = te(ids, mask, types)                      # capture + replay
+        ids2 = torch.roll(ids, 1, dims=0)
+        b = te(ids2, mask, types)                     # replay with new inputs
+        monkeypatch.setenv("LRCE_B200_BERT_GRAPH", "0")
+        a_ref, b_ref = te(ids, mask, types), te(ids2, mask, types)
+        monkeypatch.setenv("LRCE_B200_BERT_GRAPH", "1")
+        assert not te._graph_failed and len(te._graphs) >= 1
+        assert torch.equal(a, a_ref) and torch.equal(b, b_ref)
+        c = te(ids[:1], mask[:1], types[:1])          # another shape: its own graph
+        assert torch.equal(c, a_ref[:1]) or (c - a_ref[:1]).abs().max().item() < 2e-2  # batch-1 GEMMs may pick other kernels
+        w = te.bert.embeddings.word_embeddings.weight
+        old = w.detach().clone()
+        w.mul_(1.5)
+        d = te(ids, mask, types)
+        monkeypatch.setenv("LRCE_B200_BERT_GRAPH", "0")
+        d_ref = te(ids, mask, types)
+        w.copy_(old)
+        assert torch.equal(d, d_ref) and not torch.equal(d, a)
+
+
+def test_prefetch_feed_ring_delivers_every_batch():
+    """PrefetchFeed (pinned host batches -> two-slot device ring, copy of batch i+1 under the work on batch i)"""
+    from lrce_b200.feed import PrefetchFeed
+
+    dev = torch.device("cuda", 0)
+    batches = [[torch.full((4, 1024, 1024), float(i)).pin_memory(), torch.arange(8).add(i).pin_memory()] for i in range(7)]
+    seen = []
+    for x, y in PrefetchFeed(batches, dev):
+        assert x.device.type == "cuda" and y.device.type == "cuda"
+        z = x.sum() / x.numel()  # consume on the compute stream while the next copy is in flight
+        for _ in range(20):
+            z = z + (x * 0).sum()
+        seen.append((z.item(), y.cpu().tolist()))
+    assert [round(v) for v, _ in seen] == list(range(7))
+    assert [t for _, t in seen] == [list(range(i, i + 8)) for i in range(7)]

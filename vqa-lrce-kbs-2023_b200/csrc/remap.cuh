@@ -78,6 +78,36 @@ __host__ __device__ inline int slot_token_377(int slot) {
   const int w = idx % nw_c, h = (idx / nw_c) % nh_c, d = idx / (nw_c * nh_c);
   return d * 49 + (h + (ch ? 4 : 0)) * 7 + w + (cw ? 4 : 0);
 }
+// The four TMA boxes of window (hW, wW): origins of the parts before (a) / behind (b) the shift seam along h and w in the
+// UNROLLED frame. Part a is 4 long, part b 3 long; only part b can wrap around the frame border, and it wraps as a whole.
+// Mask class k = 2 [h part b] + [w part b] is box (w part, h part) = (k & 1, k >> 1) with 3 frames, landing at slot base
+// 0 / 48 / 88 / 128.
+struct WindowBoxes377 {
+  int xa, xb, ya, yb;
+};
+__host__ __device__ inline WindowBoxes377 window_boxes_377(const StageGeom& g, int hW, int wW) {
+  WindowBoxes377 b;
+  b.ya = hW * 7 + g.sh;
+  b.xa = wW * 7 + g.sw;
+  b.yb = b.ya + 4;
+  b.xb = b.xa + 4;
+  if (b.yb >= g.H) b.yb -= g.H;
+  if (b.xb >= g.W) b.xb -= g.W;
+  return b;
+}
+// flat (d*H + h)*W + w token of row / key slot `slot` as the boxes deliver it (-1 for a pad slot): box traversal order is
+// w fastest, then h, then frame
+__host__ __device__ inline int box_slot_token_377(const StageGeom& g, const WindowBoxes377& b, int slot) {
+  const int cls = (slot >= 48) + (slot >= 88) + (slot >= 128);
+  const bool ch = cls >= 2, cw = (cls & 1) != 0;
+  const int base = ch ? (cw ? 128 : 88) : (cw ? 48 : 0);
+  const int nh_c = ch ? 3 : 4, nw_c = cw ? 3 : 4;
+  const int idx = slot - base;
+  if (idx >= 3 * nh_c * nw_c) return -1;
+  const int w = idx % nw_c, h = (idx / nw_c) % nh_c, d = idx / (nw_c * nh_c);
+  return (d * g.H + (ch ? b.yb : b.ya) + h) * g.W + (cw ? b.xb : b.xa) + w;
+}
+
 // mask class of the 8-column group `grp` (0..19) of the score tile
 __host__ __device__ inline int key_group_class_377(int grp) { return (grp >= 6) + (grp >= 11) + (grp >= 16); }
 

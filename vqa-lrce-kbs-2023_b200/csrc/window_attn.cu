@@ -491,10 +491,8 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
       int seg = item / nwin, win = item - seg * nwin;
       auto coord_next = [&]() {
         Coord k;
-        k.ya = ((win >> lw) & nh_mask) * 7 + g.sh; k.xa = (win & nw_mask) * 7 + g.sw;
-        k.yb = k.ya + 4; k.xb = k.xa + 4;
-        if (k.yb >= g.H) k.yb -= g.H;
-        if (k.xb >= g.W) k.xb -= g.W;
+        const WindowBoxes377 bx = window_boxes_377(g, (win >> lw) & nh_mask, win & nw_mask);  // pinned by tests/test_remap_cpu.py
+        k.ya = bx.ya; k.xa = bx.xa; k.yb = bx.yb; k.xb = bx.xb;
         k.cq = head * 32; k.ds = seg * 3;
         if (++win == nwin) {
           win = 0;

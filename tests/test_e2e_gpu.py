@@ -133,6 +133,18 @@ def test_text_extractor_graph_replay_equals_eager(msvd, monkeypatch):
         d_ref = te(ids, mask, types)
         w.copy_(old)
         assert torch.equal(d, d_ref) and not torch.equal(d, a)
+        # capture under the agent's ambient fp16 autocast (agent_oe.py:28), replay outside of it: the graph must not hold on
+        # to autocast's cached weight copies, which die with the ambient context
+        monkeypatch.setenv("LRCE_B200_BERT_GRAPH", "1")
+        ids3, mask3, types3 = (t.repeat(2, 1)[:3].contiguous() for t in (ids, mask, types))
+        with torch.autocast("cuda", dtype=torch.float16):
+            e1 = te(ids3, mask3, types3)
+        torch.cuda.empty_cache()
+        junk = torch.randn(64, 1024, 1024, device="cuda")  # recycle whatever the ambient context released
+        e2 = te(ids3, mask3, types3)
+        del junk
+        assert torch.equal(e1, e2)
+        assert (e2[:2] - a_ref).abs().max().item() < 2e-2
 
 
 def test_prefetch_feed_ring_delivers_every_batch():

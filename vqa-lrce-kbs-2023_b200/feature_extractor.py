@@ -307,7 +307,10 @@ class TextExtractor(nn.Module):
         return new
 
     def _eager(self, input_ids, attention_mask, token_type_ids):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        # cache_enabled=False: under an ambient autocast (the reference's agents wrap the model call in one, agent_oe.py:28)
+        # the weight-cast cache outlives this context; a graph captured then would reference cached bf16 copies that are
+        # freed when the ambient context exits. Without the cache every cast is a node of the graph reading the live weights.
+        with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
             return self.bert(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids,
                              output_hidden_states=False).last_hidden_state
 

@@ -21,8 +21,10 @@
 //                           below), double-buffered, completion on mbarriers.
 //   warps 21,22  MMA      : one thread each, row tile 0 (slots 0..127) / row tile 1 (slots 128..159):
 //                           S = q k^T [M=128, N=160, K=32] (both operands K-major, 64B swizzle), then O = P v
-//                           [M=128, N=32, K=160] (v consumed MN-major exactly as TMA delivered it). Accumulators in
-//                           TMEM: S0, S1 (2 x 160 columns), O double-buffered per tile (4 x 32 columns).
+//                           [M=128, N=32, K=160] (v consumed MN-major exactly as TMA delivered it) and L = P 1
+//                           [M=128, N=16, K=160]: the row sums of the bf16 probabilities come from the tensor pipe,
+//                           which idles, not from the softmax warps, which are the bottleneck (measured: -6 %).
+//                           Accumulators in TMEM: S0, S1 (2 x 160 columns), O | L double-buffered per tile (4 x 48).
 //   warps 0-15   softmax  : row tile 0, four warps per TMEM lane quarter (thread = row, warp = 40 key columns).
 //   warps 16-19  softmax  : row tile 1. Its 32 slots are loaded FOUR times into the q tile, so every TMEM lane quarter of
 //                           S1 holds the same 32 rows and warp 16+i (lane quarter i) takes key columns [40 i, 40 i + 40):
@@ -32,11 +34,9 @@
 // memory and a 128-thread named barrier; max_j bias_ij precomputed per row by lrce_window_bias_pack) — softmax is
 // invariant to the shift, the shift mask only lowers scores, and bf16 probabilities keep their relative precision under
 // a bound that is loose by a few units. Then p = exp2(s * scale*log2e + bias + mask - m) straight into bf16 A-operand
-// tiles (double-buffered, so no warp ever waits for P v of the previous unit); every warp also sums its 40 probabilities
-// and parks the partial row sum where the other warps of the row find it one unit later (row tile 0: a TMEM column of
-// the shared lane quarter via tcgen05.st; row tile 1: shared memory), ordered by the next unit's maximum-exchange barrier.
-// The epilogue of unit j-1 (O from TMEM, 1 / row sum, 16-byte stores through the inverse remap) runs after the
-// probabilities of unit j are handed to the tensor core.
+// tiles (double-buffered, so no warp ever waits for P v of the previous unit). The epilogue of unit j-1 (O and L from
+// TMEM, 1 / row sum, 16-byte stores through the inverse remap) runs after the probabilities of unit j are handed to the
+// tensor core.
 // The S accumulator is released as soon as a warp has its 40 scores in registers, so S(j+1) is computed under the
 // softmax of unit j.
 #include "host_common.h"
@@ -49,7 +49,7 @@ constexpr int WA_N = 147;           // tokens per (3,7,7) window
 constexpr int WA_KEYS = 160;        // row / key slots of a window (class-grouped, 13 pads)
 constexpr int WA_QCOLS = 40;        // key columns per softmax thread
 constexpr int WA_BIAS_PITCH = 160;  // dense bias row pitch (bf16) = key columns of the score tile
-constexpr int WA_ON = 32;           // TMEM columns of one output buffer (head_dim)
+constexpr int WA_ON = 48;           // TMEM columns of one output buffer: 32 dims + 16 row-sum columns (L = P 1)
 constexpr int WA_THREADS = 24 * 32;
 constexpr int WA_SOFTMAX_THREADS = 20 * 32;
 constexpr int WA_WARP_LOADER = 20, WA_WARP_MMA0 = 21, WA_WARP_MMA1 = 22, WA_WARP_TMEM = 23;
@@ -71,16 +71,16 @@ constexpr int WA_OFF_P1 = WA_OFF_P0 + 2 * WA_P0_BYTES;
 constexpr int WA_OFF_BIAS = WA_OFF_P1 + 2 * WA_P1_BYTES;
 constexpr int WA_OFF_BMAX = WA_OFF_BIAS + WA_BIAS_ROWS * WA_BIAS_PITCH * 2;
 constexpr int WA_OFF_BAR = WA_OFF_BIAS + WA_BIAS_COPY_BYTES;   // mbarriers, TMEM slot, watchdog flag: 192 B
-constexpr int WA_OFF_SUM1 = WA_OFF_BAR + 192;  // float [2][3][32]: partial row sums of row tile 1 (warps 17..19 -> warp 16)
+constexpr int WA_OFF_ONES = WA_OFF_BAR + 192;  // 16 x 16 bf16 ones (B operand of L = P 1), 512 B
 constexpr int WA_OFF_M = WA_OFF_BIAS + WA_BIAS_HEAD_BYTES;     // float [2][4][128] + [2][4][32]: partial raw-score maxima
 constexpr int WA_SMEM = WA_OFF_M + (2 * 4 * 128 + 2 * 4 * 32) * 4;
-static_assert(WA_OFF_SUM1 + 2 * 3 * 32 * 4 <= WA_OFF_M, "barrier block and tile-1 sums must fit behind the bias rows");
+static_assert(WA_OFF_ONES + 512 <= WA_OFF_M && WA_OFF_ONES % 16 == 0, "barrier block and ones tile must fit behind the bias rows");
 static_assert(WA_SMEM <= 227 * 1024, "window attention shared-memory budget");
 static_assert(WA_OFF_P1 + WA_P1_BYTES + 128 * WA_KEYS * 2 <= WA_SMEM, "row tile 1's A operand must stay inside shared memory");
 
 // TMEM columns
-constexpr int WA_TM_S0 = 0, WA_TM_S1 = 160, WA_TM_O0 = 320, WA_TM_O1 = 384, WA_TM_SUM = 448, WA_TM_COLS = 512;
-static_assert(WA_TM_O1 + 2 * WA_ON <= WA_TM_SUM && WA_TM_SUM + 8 <= WA_TM_COLS, "TMEM budget");  // SUM: [2 slots][4 warps]
+constexpr int WA_TM_S0 = 0, WA_TM_S1 = 160, WA_TM_O0 = 320, WA_TM_O1 = 320 + 2 * WA_ON, WA_TM_COLS = 512;
+static_assert(WA_TM_O1 + 2 * WA_ON <= WA_TM_COLS, "TMEM budget");
 
 constexpr uint32_t WA_QK_TX_BYTES = (WA_N + 3 * 27) * 64 + WA_N * 64;  // q (class 3 four times) + k
 constexpr uint32_t WA_V_TX_BYTES = WA_N * 64;
@@ -131,16 +131,6 @@ __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
   return v;
 }
-__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -226,12 +216,10 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
   const int slot = TILE == 0 ? q * 32 + lane : 128 + lane;  // row slot of this thread
   const int prow = TILE == 0 ? slot : lane;                 // row inside the tile's P operand
   float* sMax = reinterpret_cast<float*>(smem + WA_OFF_M) + (TILE == 0 ? 0 : 2 * 4 * 128);
-  float* sSum1 = reinterpret_cast<float*>(smem + WA_OFF_SUM1);  // [2][3][32], row tile 1 only
   constexpr int mrows = TILE == 0 ? 128 : 32;
   const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
   const uint32_t s_addr = tmem_base + lane_addr + (TILE == 0 ? WA_TM_S0 : WA_TM_S1) + c * WA_QCOLS;
   const uint32_t o_base = tmem_base + lane_addr + (TILE == 0 ? WA_TM_O0 : WA_TM_O1);
-  const uint32_t sum_base = tmem_base + lane_addr + WA_TM_SUM;  // row tile 0: [2 slots][4 warps of the row]
   uint8_t* p_base = smem + (TILE == 0 ? WA_OFF_P0 : WA_OFF_P1) + core_off(prow, c * (WA_QCOLS / 8), WA_KEYS / 8);
   constexpr int p_stride = TILE == 0 ? WA_P0_BYTES : WA_P1_BYTES;
   const int tokw = slot_token_377(slot);  // window token of this row, -1 for a pad slot
@@ -267,22 +255,22 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
   const bool timing = PROF && blockIdx.x == 0 && lane == 0;
   const float MASK_L2 = -100.0f * 1.4426950408889634f;
 
-  float sum_prev = 0.f;        // tile 1, warp 16: own partial row sum of the previous unit
   bf16* dst_prev = cx.out;     // output row of the previous unit
 
-  // epilogue of unit jp: 1 / (sum of the four partial row sums), scatter through the inverse remap
+  // epilogue of unit jp: normalise by the row sum (column 32 of the output buffer, L = P 1) and scatter through the
+  // inverse remap
   auto store_o = [&](int jp) {
     timed_wait<PROF>(sh, o_full + (jp & 1), (jp >> 1) & 1, 1, jp);
     if (!stores) return;
     tcgen05_fence_after();
     const uint32_t o_addr = o_base + (jp & 1) * WA_ON;
     if (TILE == 0) {
-      uint32_t o8[8], l4[4];
-      tmem_ld_32x4(sum_base + (jp & 1) * 4, l4);
+      uint32_t o8[8];
+      const uint32_t l_u = tmem_ld_32x1(o_addr + 32);
       tmem_ld_32x8(o_addr + c * 8, o8);
       tmem_ld_wait();
       tcgen05_fence_before();
-      const float inv = 1.0f / ((__uint_as_float(l4[0]) + __uint_as_float(l4[1])) + (__uint_as_float(l4[2]) + __uint_as_float(l4[3])));
+      const float inv = 1.0f / __uint_as_float(l_u);
       uint4 o;
       o.x = pack_bf16x2(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv);
       o.y = pack_bf16x2(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv);
@@ -292,8 +280,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     } else {
       uint32_t o32[32];
       tmem_ld_32x32(o_addr, o32);
-      const float* ls = sSum1 + (jp & 1) * 96 + lane;
-      const float inv = 1.0f / ((sum_prev + ls[0]) + (ls[32] + ls[64]));
+      const float inv = 1.0f / __uint_as_float(tmem_ld_32x1(o_addr + 32));
       tmem_ld_wait();
       tcgen05_fence_before();
       if (valid) {
@@ -345,8 +332,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     __syncwarp();
     if (lane == 0) mbar_arrive(s_free);
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 4] += tc - tc0; tc0 = tc; }  // [4] TMEM load of S
-    // ---- raw-score maximum of the row: own 40 columns, then the four warps of the row through shared memory. The
-    // barrier also orders the partial row sums of unit j-1 (written before it) against their readers (store_o below).
+    // ---- raw-score maximum of the row: own 40 columns, then the four warps of the row through shared memory
     float mx = s[0];
 #pragma unroll
     for (int e = 1; e < WA_QCOLS; ++e) mx = fmaxf(mx, s[e]);
@@ -359,7 +345,6 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     // ---- p = exp2(s * scale*log2e + bias + mask - bound) -> bf16 A-operand tile (buffer j & 1: P v(j-2) has completed,
     // observed at the epilogue of unit j-2); pad columns carry a bias of -inf
     uint8_t* p_row = p_base + (j & 1) * p_stride;
-    float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
     const float2 sc2 = make_float2(cx.scale_log2e, cx.scale_log2e);
 #pragma unroll
     for (int cc = 0; cc < WA_QCOLS; cc += 8) {
@@ -373,32 +358,18 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
         const float2 t = ffma2(make_float2(s[cc + 2 * e], s[cc + 2 * e + 1]), sc2, fadd2(bf16x2_to_f32x2(bw[e]), cg2));
         p[e] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
       }
-      l01 = fadd2(l01, fadd2(p[0], p[1]));
-      l23 = fadd2(l23, fadd2(p[2], p[3]));
       uint4 u;
       u.x = pack_bf16x2(p[0].x, p[0].y); u.y = pack_bf16x2(p[1].x, p[1].y);
       u.z = pack_bf16x2(p[2].x, p[2].y); u.w = pack_bf16x2(p[3].x, p[3].y);
       *reinterpret_cast<uint4*>(p_row + (cc / 8) * 128) = u;
     }
-    const float l0 = l01.x + l01.y, l1 = l23.x + l23.y;
     fence_proxy_async_smem();  // P writes -> visible to the tensor core
     __syncwarp();
     if (lane == 0) mbar_arrive(p_full + (j & 1));
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 6] += tc - tc0; tc0 = tc; }  // [6] probabilities
-    // ---- epilogue of the previous unit (its P v was issued a whole softmax ago; its partial row sums were published
-    // before this unit's barrier). Program order puts these TMEM reads before this warp's next arrival on p_full, i.e.
-    // before P v(j+1) overwrites the same output buffer.
+    // ---- epilogue of the previous unit (its P v was issued a whole softmax ago). Program order puts these TMEM reads
+    // before this warp's next arrival on p_full, i.e. before P v(j+1) overwrites the same output buffer.
     if (j > 0) store_o(j - 1);
-    // ---- publish this unit's partial row sum (slot j & 1; its last readers ran before the barrier of unit j... j-1's
-    // epilogue above read slot (j-1) & 1, and slot j & 1 was last read in iteration j-1, before this unit's barrier)
-    if (TILE == 0) {
-      tmem_st_32x1(sum_base + (j & 1) * 4 + c, __float_as_uint(l0 + l1));
-      tmem_st_wait();
-      tcgen05_fence_before();
-    } else {
-      if (q == 0) sum_prev = l0 + l1;
-      else sSum1[((j & 1) * 3 + (q - 1)) * 32 + lane] = l0 + l1;
-    }
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 7] += tc - tc0; tc0 = tc; }  // [7] epilogue
     dst_prev = dst;
     if (++win == cx.nwin) {
@@ -406,11 +377,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
       if (++seg * cx.nwin == cx.n_items) { seg = 0; ++head; }
     }
   }
-  if (cx.n_my > 0) {
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // partial row sums of the last unit
-    if (TILE == 0) tcgen05_fence_after();
-    store_o(cx.n_my - 1);
-  }
+  if (cx.n_my > 0) store_o(cx.n_my - 1);
 }
 
 template <bool PROF>
@@ -449,6 +416,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
 
   // ---- one-time setup: zero the staging and P buffers (pad slots stay zero forever), barriers, TMEM
   for (int i = tid; i < WA_OFF_BIAS / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 32) reinterpret_cast<uint4*>(smem + WA_OFF_ONES)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (warp == WA_WARP_MMA0 && lane == 0) {
     *reinterpret_cast<volatile int*>(smem + WA_OFF_BAR + 184) = 0;  // watchdog abort flag (profiling hook only)
     for (int b = 0; b < 2; ++b) {
@@ -580,8 +548,11 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
 #pragma unroll
         for (int kk = 0; kk < WA_KEYS / 16; ++kk)  // 16 keys per step: 2 cores of P (256 B), 2 row groups of v (1024 B)
           umma_bf16_ss(tm_oj, dp + ((kk * 256) >> 4), dv + ((kk * 1024) >> 4), idesc_o, kk);
-        umma_commit(o_full + (j & 1));
         umma_commit(&sh.v_empty[j & 1]);
+#pragma unroll
+        for (int kk = 0; kk < WA_KEYS / 16; ++kk)  // L = P 1: row sums of the bf16 probabilities, columns 32..47 of the buffer
+          umma_bf16_ss(tm_oj + 32, dp + ((kk * 256) >> 4), umma_desc_nosw(smem0 + WA_OFF_ONES, 128, 256), umma_idesc_bf16(128, 16), kk);
+        umma_commit(o_full + (j & 1));
       }
     }
   } else if (warp < 20) {

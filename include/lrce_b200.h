@@ -77,6 +77,9 @@ int lrce_patch_merge_ln_bf16(const void* x, void* y, const float* gamma, const f
  * ImageNet-normalised, K ordered (c, kd, kh, kw) like the Conv3d weight, frames >= T zero (padding happens after
  * normalisation). Followed by lrce_gemm_bf16(..., LRCE_EPI_BIAS_LN). Replaces video.py:35-37 + video_swin_ori.py:472-475. */
 int lrce_patch_gather_f32(const float* clips, void* A, int n_seg, int T, int Hin, int Win, void* stream);
+/* the same for uint8 frames [n_seg, T, 3, Hin, Win] (0..255): x / 255 (torchvision ToTensor, e2e_dataset.py) is applied in
+ * the kernel, so a clip crosses PCIe as 1 byte per pixel instead of 4. */
+int lrce_patch_gather_u8(const unsigned char* clips, void* A, int n_seg, int T, int Hin, int Win, void* stream);
 
 /* Standalone cyclic shift + window partition on bf16 [n_seg, D*H*W, C] -> [n_seg*nWin*N, C] (inverse != 0: the exact
  * inverse, window_reverse + roll back). The production path fuses this map into lrce_window_attention_bf16; this entry

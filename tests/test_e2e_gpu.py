@@ -162,3 +162,13 @@ def test_prefetch_feed_ring_delivers_every_batch():
         seen.append((z.item(), y.cpu().tolist()))
     assert [round(v) for v, _ in seen] == list(range(7))
     assert [t for _, t in seen] == [list(range(i, i + 8)) for i in range(7)]
+
+
+def test_uint8_frames_give_the_fp32_logits(msvd):
+    """E2E extension: the module accepts the uint8 frames themselves; logits equal those of the ToTensor()-ed clips."""
+    _, ids, mask, types = W.make_inputs(2, 3, 32, seed=1)
+    frames = torch.randint(0, 256, (2, 3, 5, 3, 224, 224), generator=torch.Generator().manual_seed(9), dtype=torch.uint8)
+    with torch.no_grad():
+        y8 = msvd(frames.cuda(), ids.cuda(), mask.cuda(), types.cuda())
+        yf = msvd(frames.float().div(255).cuda(), ids.cuda(), mask.cuda(), types.cuda())
+    assert torch.equal(y8, yf)

@@ -159,6 +159,16 @@ def test_patch_embed(ops):
     assert rel_l2(y.view(ref.shape), ref) < 6e-3  # bf16 inputs + bf16 output rounding
 
 
+def test_patch_gather_uint8_frames_equal_totensor(ops):
+    """uint8 frames through lrce_patch_gather_u8 == torchvision ToTensor (byte -> float, / 255; e2e_dataset.py) followed by
+    the fp32 path: bit-exact (index work + the same fp32 arithmetic)."""
+    frames = torch.randint(0, 256, (3, 5, 3, 56, 84), generator=torch.Generator().manual_seed(12), dtype=torch.uint8)
+    as_float = frames.float().div(255)
+    a8 = ops.patch_gather(frames.cuda())
+    af = ops.patch_gather(as_float.cuda())
+    assert torch.equal(a8, af)
+
+
 def test_patch_merging(ops, golden):
     sd = W.make_swin_state_dict(seed=0)
     x = seeded((1, 3, 14, 14, 128), 200)

@@ -21,6 +21,7 @@ _SIGNATURES = {
     "lrce_layernorm_bf16": [_vp, _vp, _vp, _vp, _f, _ll, _i, _i, _vp],
     "lrce_patch_merge_ln_bf16": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp],
     "lrce_patch_gather_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "lrce_patch_gather_u8": [_vp, _vp, _i, _i, _i, _i, _vp],
     "lrce_window_remap_bf16": [_vp, _vp] + [_i] * 12 + [_vp],
     "lrce_remap_index": [_vp, _vp, _vp] + [_i] * 9 + [_vp],
     "lrce_window_bias_pack": [_vp, _vp, _i, _vp],

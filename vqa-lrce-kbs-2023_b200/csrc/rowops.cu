@@ -132,7 +132,15 @@ static int dispatch_ln(int C, const void* x, void* y, const float* g, const floa
 // K = (c, kd, kh, kw) ordered like the Conv3d weight; ImageNet mean/std folded into the load; frames >= T are the
 // zero padding the reference appends AFTER normalisation (video_swin_ori.py:472-473). One thread = 16 K-values.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ clips, bf16* __restrict__ A,
+// Pixel type: float in [0,1] (what torchvision's ToTensor hands the reference, e2e_dataset.py) or the uint8 frame itself
+// (x / 255 done here in fp32: same value, a quarter of the host -> device bytes).
+__device__ __forceinline__ float4 load_px4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load_px4(const uint8_t* p) {
+  const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
+  return make_float4(u.x / 255.0f, u.y / 255.0f, u.z / 255.0f, u.w / 255.0f);  // torch: byte -> float, then .div(255)
+}
+template <typename PixT>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const PixT* __restrict__ clips, bf16* __restrict__ A,
                                                            int n_seg, int T, int Hin, int Win) {
   const int D = (T + 1) / 2, Hp = Hin / 4, Wp = Win / 4;
   const long long total = static_cast<long long>(n_seg) * D * Hp * Wp * 6;
@@ -150,11 +158,11 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
   if (t < T) {
     const float mean = (c == 0) ? 0.485f : (c == 1) ? 0.456f : 0.406f;
     const float sdev = (c == 0) ? 0.229f : (c == 1) ? 0.224f : 0.225f;
-    const float* src = clips + (((n * T + t) * 3 + c) * Hin + 4 * hp) * static_cast<long long>(Win) + 4 * wp;
+    const PixT* src = clips + (((n * T + t) * 3 + c) * Hin + 4 * hp) * static_cast<long long>(Win) + 4 * wp;
     uint32_t p[8];
 #pragma unroll
     for (int kh = 0; kh < 4; ++kh) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(kh) * Win));
+      const float4 f = load_px4(src + static_cast<long long>(kh) * Win);
       // (x - mean) / std in fp32, the order torchvision Normalize uses (video.py:35), then one rounding to bf16
       p[2 * kh + 0] = pack_bf16x2((f.x - mean) / sdev, (f.y - mean) / sdev);
       p[2 * kh + 1] = pack_bf16x2((f.z - mean) / sdev, (f.w - mean) / sdev);
@@ -240,16 +248,25 @@ extern "C" int lrce_patch_merge_ln_bf16(const void* x, void* y, const float* gam
   return dispatch_ln<true, bf16>(4 * C, x, y, gamma, beta, eps, rows, D, H, W, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int lrce_patch_gather_f32(const float* clips, void* A, int n_seg, int T, int Hin, int Win, void* stream) {
+template <typename PixT>
+static int patch_gather(const PixT* clips, void* A, int n_seg, int T, int Hin, int Win, void* stream, const char* what) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
-  LRCE_REQUIRE(clips && A && n_seg > 0 && T > 0, "lrce_patch_gather_f32: bad arguments");
-  LRCE_REQUIRE(Hin % 4 == 0 && Win % 4 == 0, "lrce_patch_gather_f32: frame size %dx%d must be a multiple of the 4x4 patch", Hin, Win);
-  LRCE_REQUIRE((reinterpret_cast<uintptr_t>(clips) & 15) == 0, "lrce_patch_gather_f32: clips must be 16B aligned");
+  LRCE_REQUIRE(clips && A && n_seg > 0 && T > 0, "%s: bad arguments", what);
+  LRCE_REQUIRE(Hin % 4 == 0 && Win % 4 == 0, "%s: frame size %dx%d must be a multiple of the 4x4 patch", what, Hin, Win);
+  LRCE_REQUIRE((reinterpret_cast<uintptr_t>(clips) & (4 * sizeof(PixT) - 1)) == 0, "%s: clips must be aligned to 4 pixels", what);
   const long long total = static_cast<long long>(n_seg) * ((T + 1) / 2) * (Hin / 4) * (Win / 4) * 6;
-  patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  patch_gather_kernel<PixT><<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       clips, reinterpret_cast<bf16*>(A), n_seg, T, Hin, Win);
   return check_launch("patch_gather_kernel");
+}
+
+extern "C" int lrce_patch_gather_f32(const float* clips, void* A, int n_seg, int T, int Hin, int Win, void* stream) {
+  return patch_gather<float>(clips, A, n_seg, T, Hin, Win, stream, "lrce_patch_gather_f32");
+}
+
+extern "C" int lrce_patch_gather_u8(const unsigned char* clips, void* A, int n_seg, int T, int Hin, int Win, void* stream) {
+  return patch_gather<uint8_t>(clips, A, n_seg, T, Hin, Win, stream, "lrce_patch_gather_u8");
 }
 
 extern "C" int lrce_window_remap_bf16(const void* in, void* out, int n_seg, int D, int H, int W, int C, int wd, int wh,

@@ -186,7 +186,8 @@ class SwinTransformer3D(nn.Module):
             raise ops._lib.LrceError(f"expected clips (n, T, 3, H, W), got {tuple(clips.shape)}")
         n, T, _, Hin, Win = clips.shape
         pk = self.packed()
-        clips = clips.contiguous().float()
+        # uint8 frames (0..255) are an extension of the reference's fp32 [0,1] input: same pixels, a quarter of the PCIe bytes
+        clips = clips.contiguous() if clips.dtype == torch.uint8 else clips.contiguous().float()
         D, H, W = (T + 1) // 2, Hin // 4, Win // 4
         if D != 3 or H % 7 or W % 7:
             raise ops._lib.LrceError("the window-attention kernel needs 5/6-frame segments and H, W multiples of 28")
@@ -251,7 +252,7 @@ class SwinTransformer3D(nn.Module):
 
 class VideoExtractor(nn.Module):
     """Drop-in for lrce.feature_extractor.video.VideoExtractor (video.py:6-43).
-    forward: (B, S, T=5, 3, 224, 224) fp32 in [0,1] -> (B, S, 3, 49, 1024) bf16."""
+    forward: (B, S, T=5, 3, 224, 224) fp32 in [0,1] (or uint8 frames, an extension) -> (B, S, 3, 49, 1024) bf16."""
 
     def __init__(self, ckpt_path=None):
         super().__init__()

@@ -116,13 +116,17 @@ def patch_merge_ln(x, gamma, beta, eps, n_seg, D, H, W, C):
 
 
 def patch_gather(clips):
-    """clips fp32 (n_seg, T, 3, Hin, Win) -> bf16 [n_seg*ceil(T/2)*(Hin/4)*(Win/4), 96]."""
-    _req(clips, torch.float32, "clips")
+    """clips (n_seg, T, 3, Hin, Win), fp32 in [0,1] or the uint8 frames themselves (x / 255 is then applied in the kernel)
+    -> bf16 [n_seg*ceil(T/2)*(Hin/4)*(Win/4), 96]."""
+    if clips.dtype not in (torch.float32, torch.uint8):
+        raise _lib.LrceError(f"clips must be fp32 or uint8, got {clips.dtype}")
+    _req(clips, clips.dtype, "clips")
     assert clips.is_contiguous() and clips.dim() == 5 and clips.shape[2] == 3
     n, T, _, Hin, Win = clips.shape
     out = torch.empty((n * ((T + 1) // 2) * (Hin // 4) * (Win // 4), 96), device=clips.device, dtype=torch.bfloat16)
-    _call("lrce_patch_gather_f32", _ptr(clips), _ptr(out), n, T, Hin, Win, _stream(),
-          work=("", 2.0 * clips.numel(), 4.0 * clips.numel() + 2.0 * out.numel()))
+    sym = "lrce_patch_gather_f32" if clips.dtype == torch.float32 else "lrce_patch_gather_u8"
+    _call(sym, _ptr(clips), _ptr(out), n, T, Hin, Win, _stream(),
+          work=("", 2.0 * clips.numel(), clips.element_size() * clips.numel() + 2.0 * out.numel()))
     return out
 
 

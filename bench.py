@@ -191,7 +191,7 @@ def run_reference_arm(args):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -373,7 +373,7 @@ def run_b200_arm(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(args.config, max_seconds=25.0)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -466,11 +466,29 @@ def run_train_arm(args):
                 "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
                         "d2h_bytes_per_step": 0},
                 "clocks": clocks, "final_loss": float(loss.item())}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 if __name__ == "__main__":
+    # Native libraries print to stdout too (NCCL's "NCCL version ..." banner at communicator creation): keep the original
+    # stdout for the JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)

@@ -65,6 +65,12 @@ if which == "pick":  # the few launches worth an `ncu --set full --import-source
     torch.cuda.synchronize()
     order.append("attn s3 shift(3,3)")
 
+if which == "s2":  # the four GEMMs of a stage-2 block (K = 256 / 1024: short main loops)
+    gemm("s2.qkv", 225792, 768, 256, ops.EPI_BIAS, lnin=True)
+    gemm("s2.proj", 225792, 256, 256, ops.EPI_BIAS_RESIDUAL, stats=True)
+    gemm("s2.fc1", 225792, 1024, 256, ops.EPI_BIAS_GELU, lnin=True)
+    gemm("s2.fc2", 225792, 256, 1024, ops.EPI_BIAS_RESIDUAL, stats=True)
+
 if which == "attn1":  # one stage-3 shifted attention launch (for ncu --set full --import-source on)
     qkv = rnd(N_SEG * 588, 1536)
     bias = ops.window_bias_pack(torch.randn(2535, 16, device=dev) * 0.5)

@@ -9,6 +9,9 @@ import torch
 import lrce_b200
 from lrce_b200 import _lib, ops
 
+if os.environ.get('ATTN_LIB'):
+    _lib.LIB_PATH = os.environ['ATTN_LIB']  # A/B variants of the library (tools only)
+
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 kind = sys.argv[2] if len(sys.argv) > 2 else "oe"
 S = 3

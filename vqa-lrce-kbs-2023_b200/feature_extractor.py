@@ -341,7 +341,9 @@ class TextExtractor(nn.Module):
             cur.wait_stream(warm)
             graph = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(graph):
+                # thread_local: other threads of the process (NCCL's watchdog, a DataLoader pin-memory thread) may issue CUDA
+                # calls while this thread captures
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     static_out = self._eager(*static_in)
             except Exception as e:  # a library op that cannot be captured: stay eager from now on (still the same math)
                 self._graph_failed = True

@@ -39,22 +39,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-// same, with a suspend-time hint: the waiting thread is parked by the hardware (no issue slots, no shared-memory polling)
-// until the phase completes or ~10 ms pass, instead of spinning on try_wait
+// wait for the phase with parity `parity` to complete. try_wait carries a suspend-time hint: the waiting thread is parked by
+// the hardware (no issue slots, no shared-memory polling) until the phase completes or ~10 ms pass, instead of spinning
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"

@@ -24,6 +24,7 @@ CONFIGS = {
     "msrvtt-qa-oe": dict(kind="oe", num_classes=1500, text_seq_len=37),
     "tgif-frameqa": dict(kind="oe", num_classes=1000, text_seq_len=30),
     "tgif-action": dict(kind="mc", num_classes=1, text_seq_len=40),
+    "tgif-transition": dict(kind="mc", num_classes=1, text_seq_len=40),
     "tgif-count": dict(kind="count", num_classes=1, text_seq_len=30),
 }
 
@@ -195,6 +196,122 @@ def golden_e2e(ref):
     print("e2e.npz", sum(v.nbytes for v in out.values()))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: the remaining configs/*.json shapes, a 32-distinct-clip batch, direct pos-embed taps, BERT features, gradients
+def golden_fusion_r2(ref):
+    """LRCE heads for msrvtt-qa-oe / tgif-frameqa / tgif-transition, plus the VideoPosEmbed / TextPosEmbed outputs
+    (embedding.py:47-63, :17-23) of the msvd-qa-oe head as direct taps."""
+    out = {}
+    with torch.no_grad():
+        for name in ("msvd-qa-oe", "msrvtt-qa-oe", "tgif-frameqa", "tgif-transition"):
+            c = CONFIGS[name]
+            cls = {"oe": ref.fusionv3.LRCEOpenEnded, "mc": ref.fusionv3.LRCEMultipleChoice}[c["kind"]]
+            m = cls(768, c["num_classes"], 0.1, [7, 7], 1024, 5, [3], c["text_seq_len"])
+            # transition shares tgif-action's shapes: a different weight seed makes it a distinct case
+            seed = 1 if name == "tgif-transition" else 0
+            m.load_state_dict(weights.make_fusion_state_dict(c["num_classes"], c["text_seq_len"], 3, seed=seed), strict=True)
+            m.eval()
+            B = 2
+            vf = seeded((B, 3, 3, 49, 1024), 310)
+            tshape = (B, 5, c["text_seq_len"], 768) if c["kind"] == "mc" else (B, c["text_seq_len"], 768)
+            tf = seeded(tshape, 311)
+            taps, toks, hooks = {}, [], []
+            hooks.append(m.fusion_transformer.fusion_layer_norm.register_forward_hook(lambda mod, i, o: toks.append(o.clone())))
+            if name == "msvd-qa-oe":
+                hooks.append(m.video_pos_embed.register_forward_hook(lambda mod, i, o: taps.__setitem__("video_embedded", o.clone())))
+                hooks.append(m.question_pos_embed.register_forward_hook(lambda mod, i, o: taps.__setitem__("text_embedded", o.clone())))
+            y = m(vf, tf, torch.ones(tshape[:-1], dtype=torch.int64))
+            for h in hooks:
+                h.remove()
+            out[f"{name}.logits"] = y.numpy()
+            out[f"{name}.tokens"] = torch.stack(toks).numpy()
+            for k, v in taps.items():
+                out[f"{name}.{k}"] = v.numpy().astype(np.float16) if k == "video_embedded" else v.numpy()
+    np.savez_compressed(os.path.join(OUT, "fusion_r2.npz"), **out)
+    print("fusion_r2.npz", sum(v.nbytes for v in out.values()))
+
+
+def golden_e2e_r2(ref):
+    """whole E2E forward, B=2, for msrvtt-qa-oe (configs[2]), tgif-frameqa (configs[4]) and tgif-transition; BERT's
+    last_hidden_state (text.py:11-17) in full for msvd-qa-oe and as a sample for the multiple-choice shape."""
+    out = {}
+    with torch.no_grad():
+        for name in ("msvd-qa-oe", "msrvtt-qa-oe", "tgif-frameqa", "tgif-transition"):
+            c = CONFIGS[name]
+            sd = weights.make_e2e_state_dict(c["num_classes"], c["text_seq_len"], 3, seed=0)
+            m = ref_harness.build_reference_e2e(c["kind"], model_cfg(c), sd)
+            n_cand = 5 if c["kind"] == "mc" else 0
+            clips, ids, mask, types = weights.make_inputs(2, 3, c["text_seq_len"], seed=3 if name == "tgif-transition" else 1,
+                                                          n_candidates=n_cand)
+            if name == "msvd-qa-oe":
+                out[f"{name}.text_features"] = m.text_extractor(ids, mask, types).numpy()
+                del m
+                continue
+            text = []
+            h = m.text_extractor.register_forward_hook(lambda mod, i, o: text.append(o))
+            y = m(clips, ids, mask, types)
+            h.remove()
+            out[f"{name}.logits"] = y.numpy()
+            out[f"{name}.text_features.sample"] = sample(text[0])
+            print(name, "logits", tuple(y.shape), "argmax", y.argmax(-1).tolist())
+            del m
+    np.savez_compressed(os.path.join(OUT, "e2e_r2.npz"), **out)
+    print("e2e_r2.npz", sum(v.nbytes for v in out.values()))
+
+
+def golden_e2e_b32(ref):
+    """configs[1]: 32 DISTINCT clips + questions through the reference E2EOpenEnded (fp32, CPU): logits for the top-1
+    agreement figure over 32 clips."""
+    c = CONFIGS["msvd-qa-oe"]
+    sd = weights.make_e2e_state_dict(c["num_classes"], c["text_seq_len"], 3, seed=0)
+    m = ref_harness.build_reference_e2e(c["kind"], model_cfg(c), sd)
+    clips, ids, mask, types = weights.make_inputs(32, 3, c["text_seq_len"], seed=2)
+    ys, fs = [], []
+    h = m.video_extractor.register_forward_hook(lambda mod, i, o: fs.append(o))
+    with torch.no_grad():
+        for b0 in range(0, 32, 4):
+            ys.append(m(clips[b0:b0 + 4], ids[b0:b0 + 4], mask[b0:b0 + 4], types[b0:b0 + 4]))
+    h.remove()
+    y, f = torch.cat(ys), torch.cat(fs)
+    out = {"msvd-qa-oe.logits": y.numpy(), "msvd-qa-oe.video_features.sample": sample(f),
+           "msvd-qa-oe.video_features.moments": moments(f)}
+    print("b32 argmax", y.argmax(-1).tolist(), "distinct", len(set(y.argmax(-1).tolist())))
+    top2 = y.topk(2, dim=-1).values
+    print("top1-top2 margins: min %.3f median %.3f" % ((top2[:, 0] - top2[:, 1]).min().item(), (top2[:, 0] - top2[:, 1]).median().item()))
+    np.savez_compressed(os.path.join(OUT, "e2e_b32.npz"), **out)
+    print("e2e_b32.npz", sum(v.nbytes for v in out.values()))
+
+
+GRAD_STRIDE = 1999
+
+
+def golden_grad(ref):
+    """configs[4] (tgif-frameqa) training step of the reference LRCEOpenEnded with drop_out_rate=0 (dropout RNG cannot be
+    matched): cross-entropy loss, backward; per-parameter gradient norms + strided samples."""
+    c = CONFIGS["tgif-frameqa"]
+    m = ref.fusionv3.LRCEOpenEnded(768, c["num_classes"], 0.0, [7, 7], 1024, 5, [3], c["text_seq_len"])
+    m.load_state_dict(weights.make_fusion_state_dict(c["num_classes"], c["text_seq_len"], 3, seed=0), strict=True)
+    m.train()
+    B = 4
+    vf = seeded((B, 3, 3, 49, 1024), 320)
+    tf = seeded((B, c["text_seq_len"], 768), 321)
+    target = torch.tensor([3, 7, 11, 500])
+    y = m(vf, tf, torch.ones((B, c["text_seq_len"]), dtype=torch.int64))
+    loss = torch.nn.functional.cross_entropy(y, target)
+    loss.backward()
+    out = {"logits": y.detach().numpy(), "loss": np.array([loss.item()]), "target": target.numpy()}
+    names, norms = [], []
+    for k, p in m.named_parameters():
+        names.append(k)
+        norms.append(p.grad.double().norm().item())
+        out["g." + k] = p.grad.reshape(-1)[::GRAD_STRIDE].numpy().copy()
+    out["names"] = np.array(names)
+    out["norms"] = np.array(norms)
+    print("grad golden: loss %.4f, %d params, total grad norm %.4f" % (loss.item(), len(names), float(np.sqrt((np.array(norms) ** 2).sum()))))
+    np.savez_compressed(os.path.join(OUT, "grad.npz"), **out)
+    print("grad.npz", sum(v.nbytes for v in out.values()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -208,3 +325,6 @@ if __name__ == "__main__":
         golden_fusion(ref)
     if "e2e" in which:
         golden_e2e(ref)
+    for key, fn in (("fusion_r2", golden_fusion_r2), ("e2e_r2", golden_e2e_r2), ("e2e_b32", golden_e2e_b32), ("grad", golden_grad)):
+        if key in which or not sys.argv[1:]:
+            fn(ref)

@@ -130,3 +130,79 @@ def test_e2e_mc_count_b2(golden, name, kind, ncls, L):
     with torch.no_grad():
         y = O.e2e_forward(sd, clips, ids, mask, types, kind)
     close(y, golden["e2e"][f"{name}.logits"], rtol=2e-3, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round-2 fixtures (oracle/make_golden.py golden_*_r2 / golden_e2e_b32 / golden_grad): the remaining configs/*.json
+# shapes, direct pos-embed taps, BERT features, a 32-distinct-clip batch (first clips here, all 32 on the GPU) and the
+# gradients of the configs[4] training step
+R2 = [("msvd-qa-oe", "oe", 1000, 32, 0), ("msrvtt-qa-oe", "oe", 1500, 37, 0), ("tgif-frameqa", "oe", 1000, 30, 0),
+      ("tgif-transition", "mc", 1, 40, 1)]
+
+
+@pytest.mark.parametrize("name,kind,ncls,L,seed", R2)
+def test_fusion_heads_r2(golden, name, kind, ncls, L, seed):
+    g = golden["fusion_r2"]
+    sd = W.make_fusion_state_dict(ncls, L, 3, seed=seed)
+    vf = seeded((2, 3, 3, 49, 1024), 310)
+    tf = seeded((2, 5, L, 768) if kind == "mc" else (2, L, 768), 311)
+    taps = {}
+    y = O.lrce_head(sd, vf, tf, kind, pre="", taps=taps)
+    close(y, g[f"{name}.logits"], rtol=1e-3, atol=1e-3)
+    close(torch.stack([taps[f"token.s{s}"] for s in range(3)]), g[f"{name}.tokens"], rtol=1e-3, atol=1e-3)
+    if name == "msvd-qa-oe":  # VideoPosEmbed / TextPosEmbed outputs (embedding.py:47-63, :17-23) asserted directly
+        close(taps["text_embedded"], g[f"{name}.text_embedded"], rtol=1e-4, atol=1e-4)
+        close(taps["video_embedded"], torch.from_numpy(g[f"{name}.video_embedded"].astype(np.float32)), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("name,kind,ncls,L,in_seed", [("msrvtt-qa-oe", "oe", 1500, 37, 1), ("tgif-frameqa", "oe", 1000, 30, 1),
+                                                      ("tgif-transition", "mc", 1, 40, 3)])
+def test_e2e_r2_b2(golden, name, kind, ncls, L, in_seed):
+    """BASELINE.json configs[2] (msrvtt-qa-oe), configs[4]'s model (tgif-frameqa) and tgif-transition, batch 2, fp32 CPU."""
+    g = golden["e2e_r2"]
+    sd = W.make_e2e_state_dict(ncls, L, 3, seed=0)
+    clips, ids, mask, types = W.make_inputs(2, 3, L, seed=in_seed, n_candidates=5 if kind == "mc" else 0)
+    taps = {}
+    with torch.no_grad():
+        y = O.e2e_forward(sd, clips, ids, mask, types, kind, taps=taps)
+    close(y, g[f"{name}.logits"], rtol=2e-3, atol=2e-3)
+    close(taps["text_features"].reshape(-1)[::997], g[f"{name}.text_features.sample"], rtol=2e-3, atol=2e-3)
+
+
+def test_bert_features_full(golden):
+    sd = W.make_e2e_state_dict(1000, 32, 3, seed=0)
+    _, ids, mask, types = W.make_inputs(2, 3, 32, seed=1)
+    with torch.no_grad():
+        t = O.bert_forward(sd, ids, mask, types)
+    close(t, golden["e2e_r2"]["msvd-qa-oe.text_features"], rtol=2e-3, atol=2e-3)
+
+
+def test_e2e_b32_first_clips(golden):
+    """the first 4 of the 32 distinct clips of tests/golden/e2e_b32.npz (the GPU suite checks all 32)"""
+    sd = W.make_e2e_state_dict(1000, 32, 3, seed=0)
+    clips, ids, mask, types = W.make_inputs(32, 3, 32, seed=2)
+    with torch.no_grad():
+        y = O.e2e_forward(sd, clips[:4], ids[:4], mask[:4], types[:4], "oe")
+    close(y, golden["e2e_b32"]["msvd-qa-oe.logits"][:4], rtol=2e-3, atol=2e-3)
+
+
+def test_training_step_gradients(golden):
+    """configs[4]: gradients of the cross-entropy loss w.r.t. every encoder parameter, oracle autograd vs the reference
+    LRCEOpenEnded with drop_out_rate=0 (oracle/make_golden.py golden_grad)."""
+    g = golden["grad"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in W.make_fusion_state_dict(1000, 30, 3, seed=0).items()}
+    y = O.lrce_head(sd, seeded((4, 3, 3, 49, 1024), 320), seeded((4, 30, 768), 321), "oe", pre="")
+    loss = torch.nn.functional.cross_entropy(y, torch.from_numpy(g["target"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"][0])) < 1e-3
+    close(y.detach(), g["logits"], rtol=1e-3, atol=1e-3)
+    for name, norm in zip(g["names"].tolist(), g["norms"].tolist()):
+        gr = sd[name].grad
+        if name.endswith(("self_attn.in_proj_weight", "self_attn.in_proj_bias")):
+            # length-1 self-attention: q and k rows receive exactly zero gradient (softmax over one key)
+            assert gr is None or gr[: 2 * 768].abs().max().item() == 0.0
+        got = torch.zeros_like(sd[name]) if gr is None else gr
+        ref = torch.from_numpy(g["g." + name])
+        samp = got.reshape(-1)[::1999]
+        assert (samp - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item()) + 1e-5, name
+        assert abs(got.double().norm().item() - norm) <= 2e-3 * max(norm, 1e-3) + 1e-5, name

@@ -41,7 +41,9 @@ GFLOP_PER_CLIP = 303.96  # Swin-B 3 x 96.354 + canonical encode
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
-GEMM_DRAM_BYTES_PER_STEP = 17607.3e6 + 12948.1e6  # gemm_tc_kernel family, one batch-32 forward (ncu launch list v3)
+GEMM_DRAM_BYTES_PER_STEP = 17607.3e6 + 12948.1e6  # gemm_tc_kernel family, one batch-32 forward (ncu launch list)
+GEMM_LAUNCHES_NCU = 103.0
+GEMM_TRAFFIC_SOURCE = "profiles/r01_launches_v3_summary.md"
 
 
 def load_peaks():
@@ -152,46 +154,123 @@ def synth_inputs(batch, cfg, seed):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_baseline(cfg_name, max_seconds=25.0, batch=2):
-    """times the CPU oracle (port of the reference's fp32 CPU path) on all host cores; bounded sample."""
+def _cpu_forward_fn(cfg_name, batch):
+    """(callable running ONE batch-`batch` E2E forward on the host cores, kind, description). The unmodified reference
+    (its own E2E* modules imported from baseline/_ref or /root/reference through oracle/ref_harness.py) when a copy is
+    present — kind "reference"; otherwise the oracle port (oracle/lrce_oracle.py) — kind "port"."""
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import lrce_oracle as O
+    import ref_harness
     import weights as W
 
     cfg = CONFIGS[cfg_name]
+    sd = W.make_e2e_state_dict(cfg["num_classes"], cfg["text_seq_len"], 3, seed=0)
+    inputs = W.make_inputs(batch, 3, cfg["text_seq_len"], seed=1, n_candidates=5 if cfg["kind"] == "mc" else 0)
+    if ref_harness.find_reference() is not None:
+        try:
+            model = ref_harness.build_reference_e2e(cfg["kind"], model_kwargs(cfg), sd)
+            return (lambda: model(*inputs)), "reference", "the unmodified reference E2E module (fp32, torch CPU)"
+        except Exception as e:  # a broken copy must not take the bench down: fall back to the port and say so
+            sys.stderr.write(f"[bench] reference import failed ({type(e).__name__}: {e}); timing the oracle port\n")
+    return (lambda: O.e2e_forward(sd, *inputs, cfg["kind"])), "port", "oracle/lrce_oracle.py (fp32, torch CPU)"
+
+
+def cpu_baseline(cfg_name, steps=3, warmup=1, batch=2, max_seconds=None):
+    """times the reference's CPU path on all host cores: `warmup` untimed + exactly `steps` timed batch-`batch` forwards
+    (mean). `max_seconds` bounds the sample for the in-line cpu_baseline of the B200 arm (fewer steps, never zero)."""
+    import torch
+
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = W.make_e2e_state_dict(cfg["num_classes"], cfg["text_seq_len"], 3, seed=0)
-    clips, ids, mask, types = W.make_inputs(batch, 3, cfg["text_seq_len"], seed=1, n_candidates=5 if cfg["kind"] == "mc" else 0)
+    fwd, kind, what = _cpu_forward_fn(cfg_name, batch)
     times = []
     t_start = time.time()
     with torch.no_grad():
-        O.e2e_forward(sd, clips, ids, mask, types, cfg["kind"])  # warm-up
-        while len(times) < 5 and (time.time() - t_start) < max_seconds:
+        for _ in range(warmup):
+            fwd()
+        for _ in range(steps):
             t0 = time.time()
-            O.e2e_forward(sd, clips, ids, mask, types, cfg["kind"])
+            fwd()
             times.append(time.time() - t0)
-    best = min(times)
-    return {"value": batch / best, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"{cfg_name} E2E forward, batch {batch} fp32, best of {len(times)} after 1 warm-up "
-                      f"(oracle/lrce_oracle.py on torch CPU, {cores} threads)"}, best
+            if max_seconds is not None and time.time() - t_start > max_seconds:
+                break
+    mean = sum(times) / len(times)
+    return {"value": batch / mean, "unit": "clips/s", "cores": cores, "kind": kind,
+            "sample": f"{cfg_name} E2E forward, batch {batch} fp32, mean of {len(times)} forwards after {warmup} warm-up: "
+                      f"{what}, {cores} threads"}, mean, len(times)
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, best = cpu_baseline(args.config, max_seconds=max(20.0, 12.0 * (args.steps + args.warmup)), batch=2)
+    base, mean, n = cpu_baseline(args.config, steps=args.steps, warmup=args.warmup, batch=2)
     line = {"impl": "reference", "metric": "clips/sec LRCE fwd", "value": base["value"], "unit": "clips/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3,
+            "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": mean * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config} E2E eval forward (CPU, batch 2 sample of the batch-{args.batch} workload)"},
+            "config": {"workload": f"{args.config} E2E eval forward (CPU; each step = a batch-2 sample of the batch-{args.batch} "
+                                   "workload)"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def torch_eager_on_b200(cfg_name, batch, dev, steps=5, warmup=2):
+    """the reference's own modules on the same B200 — torch eager library kernels (cuBLAS / cuDNN / ATen)
+    under the agent's fp16 autocast (agent_oe.py:28), device-resident inputs. This is the "PyTorch on the same box" bar
+    the hand-written kernels are measured against; it needs a copy of the reference (baseline/_ref)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness
+    import weights as W
+
+    if ref_harness.find_reference() is None:
+        return {"unavailable": "no copy of the reference under baseline/_ref (made by __graft_entry__.build() in the build container)"}
+    cfg = CONFIGS[cfg_name]
+    try:
+        sd = W.make_e2e_state_dict(cfg["num_classes"], cfg["text_seq_len"], 3, seed=0)
+        model = ref_harness.build_reference_e2e(cfg["kind"], model_kwargs(cfg), sd).to(dev).eval()
+        inputs = [t.to(dev) for t in synth_inputs(batch, cfg, seed=1)]
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            for _ in range(warmup):
+                model(*inputs)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model(*inputs)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del model
+        torch.cuda.empty_cache()
+        return {"value": batch / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "what": f"unmodified reference {cfg_name} E2E module, torch {torch.__version__} eager, fp16 autocast, batch {batch}, "
+                        "inputs resident in HBM"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores local to GPU `index` (NVML's ideal affinity) BEFORE the pinned host buffers are
+    allocated, so that they are first-touched on the NUMA node the GPU's PCIe root hangs off: on two-socket hosts a remote
+    pinned buffer halves the H2D rate of the 289 MB fp32 batch (the e2e figure's box-to-box spread in round 1)."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cores_before": before, "cores_after": len(os.sched_getaffinity(0)), "bound": True}
+    except Exception as e:
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -215,13 +294,13 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     cfg = CONFIGS[args.config]
     cls = {"oe": lrce_b200.E2EOpenEnded, "mc": lrce_b200.E2EMultipleChoice, "count": lrce_b200.E2ECount}[cfg["kind"]]
+    numa = bind_to_gpu_numa_node(local)
     torch.manual_seed(0)
     model = cls(pretrained=False, **model_kwargs(cfg)).to(dev).eval()
     B = args.batch
     host = [t.pin_memory() for t in synth_inputs(B, cfg, seed=1 + rank)]
     devin = [t.to(dev) for t in host]
     n_out = (B, 5) if cfg["kind"] == "mc" else ((B,) if cfg["kind"] == "count" else (B, cfg["num_classes"]))
-    gathered = torch.empty((world,) + n_out, device=dev) if world > 1 else None
     host_out = torch.empty(n_out, dtype=torch.float32).pin_memory()
 
     def step(inputs):
@@ -270,6 +349,8 @@ def run_b200_arm(args):
     for cur in PrefetchFeed([host] * 2, dev):
         step(cur)
     barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for cur in PrefetchFeed([host] * args.steps, dev):
@@ -278,6 +359,17 @@ def run_b200_arm(args):
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    clocks_e2e = sampler.stop()
+    # copy-only timing of the same batches (no compute): attributes an e2e shortfall to PCIe / host memory vs everything else
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_copy = min(args.steps, 10)
+    c0.record()
+    for _ in range(n_copy):
+        for d, h in zip(devin, host):
+            d.copy_(h, non_blocking=True)
+    c1.record()
+    barrier()
+    ms_h2d = c0.elapsed_time(c1) / n_copy
 
     # ---- timed region 3 (extra, not the contract's e2e): the same end-to-end loop fed with the uint8 frames themselves
     # (the module's extension over the reference's ToTensor()-ed fp32 clips: x / 255 happens in the first kernel), i.e. a
@@ -286,6 +378,8 @@ def run_b200_arm(args):
     for cur in PrefetchFeed([host8] * 2, dev):
         step(cur)
     barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record()
     for cur in PrefetchFeed([host8] * args.steps, dev):
@@ -294,6 +388,16 @@ def run_b200_arm(args):
     e5.record()
     barrier()
     ms_e2e8 = e4.elapsed_time(e5)
+    clocks_e2e8 = sampler.stop()
+    # device-resident steps once more, now that the board has been under load for seconds: separates the clock droop of the
+    # later regions from anything the host feed costs
+    e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e6.record()
+    for _ in range(args.steps):
+        step(devin)
+    e7.record()
+    barrier()
+    ms_late = e6.elapsed_time(e7)
 
     t = torch.tensor([ms, ms_e2e, ms_e2e8], device=dev, dtype=torch.float64)
     if world > 1:
@@ -340,9 +444,13 @@ def run_b200_arm(args):
                        "global_batch": world * B, "parallelism": f"clip-sharded dp{world}" + (" + NCCL logit all_gather" if world > 1 else ""),
                        "l2_policy": "inputs (289 MB of fp32 clips per step) and every stage tensor exceed the 126 MB L2"},
             "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": host_out.numel() * 4},
+                    "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e,
+                    "h2d_only_ms_per_step": ms_h2d, "h2d_only_gbs": h2d / ms_h2d / 1e6,
+                    "device_resident_ms_per_step_after_load": ms_late / args.steps,
+                    "host_numa_binding": numa},
             "e2e_uint8_frames": {"value": world * B * args.steps / (ms_e2e8 / 1e3), "unit": "clips/s",
                                  "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host8),
+                                 "ms_per_step": ms_e2e8 / args.steps, "clocks": clocks_e2e8,
                                  "note": "extension: uint8 frames as the module input (x/255 in the first kernel); not the "
                                          "reference-API e2e above"},
             "gpu_launches": gpu_launches,
@@ -350,11 +458,11 @@ def run_b200_arm(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all Linear layers)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": f"{peaks['source']} bf16_tflops_sustained",
-                         # DRAM bytes (read + write) per launch, mean over the 103 GEMM launches of one forward, from the
-                         # committed ncu launch list (profiles/r01_launches_v3_summary.md: 17.61 GB read + 12.95 GB written)
-                         "traffic": GEMM_DRAM_BYTES_PER_STEP / 103.0 if args.config == "msvd-qa-oe" and B == 32 else None,
-                         "traffic_note": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                                         "profiles/r01_launches_v3_summary.md",
+                         # DRAM bytes (read + write) per launch, mean over the GEMM launches of one forward: a STATIC figure
+                         # from the committed ncu launch list of this kernel set, not measured in this run
+                         "traffic": GEMM_DRAM_BYTES_PER_STEP / GEMM_LAUNCHES_NCU if args.config == "msvd-qa-oe" and B == 32 else None,
+                         "traffic_note": "static: bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum over the GEMM "
+                                         "launches of " + GEMM_TRAFFIC_SOURCE,
                          "algorithmic_bytes_per_launch": g.get("bytes", 0.0) / max(g["launches"], 1),
                          "launches_per_step": g["launches"] / args.steps, "share_of_step": g["ms"] / ms,
                          "whole_forward_tflops": clips_per_s / world * GFLOP_PER_CLIP / 1e3,
@@ -372,7 +480,13 @@ def run_b200_arm(args):
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline(args.config, max_seconds=25.0)
+            line["cpu_baseline"], _, _ = cpu_baseline(args.config, steps=10, warmup=1, max_seconds=25.0)
+        if world == 1 and not args.no_eager:
+            del model
+            torch.cuda.empty_cache()
+            line["torch_eager_b200"] = torch_eager_on_b200(args.config, B, dev)
+            if "value" in line["torch_eager_b200"]:
+                line["torch_eager_b200"]["speedup_of_this_repo"] = clips_per_s / line["torch_eager_b200"]["value"]
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -497,6 +611,7 @@ if __name__ == "__main__":
     ap.add_argument("--config", default="msvd-qa-oe", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-on-B200 figure (reference modules, fp16 autocast)")
     ap.add_argument("--train", action="store_true", help="time the configs[4] training step instead of the eval forward")
     a = ap.parse_args()
     if a.impl == "reference":

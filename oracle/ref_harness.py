@@ -64,8 +64,58 @@ def _install_stubs():
     if "h5py" not in sys.modules:
         sys.modules["h5py"] = types.ModuleType("h5py")
     if "cosine_annealing_warmup" not in sys.modules:
+        import math
+
+        class CosineAnnealingWarmupRestarts(torch.optim.lr_scheduler.LRScheduler):
+            """stand-in for the un-vendored pip-from-git dependency (readme.md:11, agent_base.py:5,56-64): linear warm-up to
+            max_lr, cosine decay to min_lr, restart every first_cycle_steps * cycle_mult^k steps with max_lr *= gamma.
+            Every param group follows the same schedule, as in the published implementation."""
+
+            def __init__(self, optimizer, first_cycle_steps, cycle_mult=1.0, max_lr=0.1, min_lr=0.001, warmup_steps=0,
+                         gamma=1.0, last_epoch=-1):
+                self.first, self.mult, self.base_max, self.max_lr = first_cycle_steps, cycle_mult, max_lr, max_lr
+                self.min_lr, self.warm, self.gamma = min_lr, warmup_steps, gamma
+                self.cur, self.cycle, self.step_in_cycle = first_cycle_steps, 0, last_epoch
+                super().__init__(optimizer, last_epoch)
+                for g in self.optimizer.param_groups:
+                    g["lr"] = self.min_lr
+
+            def get_lr(self):
+                if self.step_in_cycle < 0:
+                    return [self.min_lr for _ in self.optimizer.param_groups]
+                if self.step_in_cycle < self.warm:
+                    lr = (self.max_lr - self.min_lr) * self.step_in_cycle / max(self.warm, 1) + self.min_lr
+                else:
+                    t = (self.step_in_cycle - self.warm) / max(self.cur - self.warm, 1)
+                    lr = self.min_lr + (self.max_lr - self.min_lr) * (1 + math.cos(math.pi * t)) / 2
+                return [lr for _ in self.optimizer.param_groups]
+
+            def step(self, epoch=None):
+                if epoch is None:
+                    epoch = self.last_epoch + 1
+                    self.step_in_cycle += 1
+                    if self.step_in_cycle >= self.cur:
+                        self.cycle += 1
+                        self.step_in_cycle -= self.cur
+                        self.cur = int((self.cur - self.warm) * self.mult) + self.warm
+                else:
+                    if epoch >= self.first:
+                        if self.mult == 1.0:
+                            self.step_in_cycle, self.cycle = epoch % self.first, epoch // self.first
+                        else:
+                            n = int(math.log(epoch / self.first * (self.mult - 1) + 1, self.mult))
+                            self.cycle = n
+                            self.step_in_cycle = epoch - int(self.first * (self.mult ** n - 1) / (self.mult - 1))
+                            self.cur = self.first * self.mult ** n
+                    else:
+                        self.cur, self.step_in_cycle = self.first, epoch
+                self.max_lr = self.base_max * (self.gamma ** self.cycle)
+                self.last_epoch = math.floor(epoch)
+                for g, lr in zip(self.optimizer.param_groups, self.get_lr()):
+                    g["lr"] = lr
+
         caw = types.ModuleType("cosine_annealing_warmup")
-        caw.CosineAnnealingWarmupRestarts = object
+        caw.CosineAnnealingWarmupRestarts = CosineAnnealingWarmupRestarts
         sys.modules["cosine_annealing_warmup"] = caw
 
 
@@ -92,6 +142,14 @@ def import_reference():
     _imported.update(root=root, swin=swin, VideoExtractor=VideoExtractor, e2e=e2e, embedding=embedding,
                      fusionv3=fusionv3)
     return types.SimpleNamespace(**_imported)
+
+
+def import_agents():
+    """the reference's agents (lrce/agent/*.py: AgentOE / AgentMC / AgentCount), imported unmodified"""
+    import_reference()
+    from lrce.agent import AgentCount, AgentMC, AgentOE
+
+    return types.SimpleNamespace(AgentOE=AgentOE, AgentMC=AgentMC, AgentCount=AgentCount)
 
 
 @contextlib.contextmanager

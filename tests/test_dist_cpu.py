@@ -31,6 +31,13 @@ def _worker(rank, world, port, n_clips, result_dir):
     assert hi - lo == n_clips // world  # equal shards in this test (all_gather_into_tensor needs equal shapes)
     gathered = D.gather_logits(logits_all[lo:hi].clone())
     assert torch.equal(gathered, logits_all)
+    # ragged last batch: shard_range hands out shards that differ by one; the gather pads and trims
+    odd = torch.randn(n_clips - 1, 7, generator=g)
+    lo2, hi2 = D.shard_range(n_clips - 1, rank, world)
+    sizes = [b - a for a, b in (D.shard_range(n_clips - 1, r, world) for r in range(world))]
+    assert len(set(sizes)) == 2
+    assert torch.equal(D.gather_logits(odd[lo2:hi2].clone()), odd)                # sizes exchanged by the call
+    assert torch.equal(D.gather_logits(odd[lo2:hi2].clone(), sizes=sizes), odd)   # sizes supplied by the caller
 
     # ---- gradient all-reduce: per-rank grads of a per-rank loss average to the full-batch gradient
     torch.manual_seed(1)

@@ -1,0 +1,156 @@
+"""GPU: proof of the drop-in claim (north_star: "the existing model/agent API that eval.py and train_ddp.py call stays
+unchanged"). The UNMODIFIED reference agents (lrce/agent/agent_base.py, agent_oe.py, agent_mc.py — imported from the
+git-ignored copy under baseline/_ref that `__graft_entry__.build()` makes, or from /root/reference) drive the B200 modules
+exactly as eval.py:53-90 / train_ddp.py:89-130 do: `from lrce.models.e2e import E2E*` after `lrce_b200.install()`, model
+construction with the reference's keyword arguments (Swin checkpoint in the `backbone.` layout on disk, video.py:20-26),
+`Agent*(model, rank, args, ...)` -> `.to(gpu)` + plain `DDP(model)` over single-rank NCCL, `load_checkpoint`,
+`do_evaluation(DataLoader(..., sampler=DistributedSampler))` under the agent's fp16 autocast, training iterations through
+`scaler.scale(loss).backward()` with the L2 term, and a `save_checkpoint` / `load_checkpoint` round trip.
+Skipped when no copy of the reference is present."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import ref_harness  # noqa: E402
+import weights as W  # noqa: E402
+
+needs_ref = pytest.mark.skipif(ref_harness.find_reference() is None, reason="no copy of the reference (baseline/_ref)")
+CFG = dict(feature_dim=768, video_feature_res=[7, 7], video_feature_dim=1024, frame_sample_size=5, temporal_scale=[3])
+
+
+@pytest.fixture(scope="module")
+def nccl_single_rank():
+    import torch.distributed as dist
+
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "12355")  # eval.py:12
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", rank=0, world_size=1)
+        created = True
+    yield
+    if created:
+        dist.destroy_process_group()
+
+
+def agent_args(tmp_path, dataset, **over):
+    """the Namespace eval.py / train_ddp.py hand to the agent (args.py:10-155 defaults + configs/<dataset>.json)"""
+    ns = argparse.Namespace(
+        dataset=dataset, lr=[1e-5, 1e-5, 1e-5], min_lr=1e-7, use_cosine_scheduler=True, lr_restart_epoch=2,
+        lr_restart_mul=1, lr_warm_up=0, lr_decay_factor=0.5, patience=2, reg_strength=1e-4, epoch=1, ckpt_interval=1,
+        log_dir=str(tmp_path), debug_mode=False, batch_size=2, num_workers=0)
+    for k, v in over.items():
+        setattr(ns, k, v)
+    return ns
+
+
+def loader(tensors, batch_size=2):
+    from torch.utils.data import DataLoader, TensorDataset
+    from torch.utils.data.distributed import DistributedSampler
+
+    ds = TensorDataset(*tensors)
+    return DataLoader(ds, batch_size=batch_size, shuffle=False, num_workers=0, pin_memory=True, sampler=DistributedSampler(ds))
+
+
+@needs_ref
+def test_reference_agent_oe_eval_train_checkpoint(golden, tmp_path, nccl_single_rank):
+    import lrce_b200
+
+    agents = ref_harness.import_agents()          # unmodified lrce.agent.* (and lrce.lib's star imports)
+    lrce_b200.install()                           # eval.py:5 now resolves to the B200 classes
+    from lrce.models.e2e import E2EOpenEnded
+    assert E2EOpenEnded is lrce_b200.E2EOpenEnded
+
+    sd = W.make_e2e_state_dict(1000, 32, 3, seed=0)
+    swin_sd = {k[len("video_extractor.swin."):]: v for k, v in sd.items() if k.startswith("video_extractor.swin.")}
+    with ref_harness.reference_workdir(swin_sd):  # ./pretrained_models/swin_base_...pth in the `backbone.` layout
+        model = E2EOpenEnded(num_classes=1000, text_seq_len=32, **CFG)   # eval.py:66-74 keywords; pretrained path
+    # the Swin checkpoint on disk went through VideoExtractor's `backbone.` loader (video.py:20-26)
+    assert torch.equal(model.video_extractor.swin.layers[2].blocks[7].mlp.fc1.weight.detach().cpu(),
+                       sd["video_extractor.swin.layers.2.blocks.7.mlp.fc1.weight"])
+
+    # ---- eval.py:77-90: evaluator agent, checkpoint, DistributedSampler loader, do_evaluation
+    ckpt = tmp_path / "seeded.pt"
+    torch.save({"model_state_dict": sd}, ckpt)
+    ev = agents.AgentOE(model, 0, agent_args(tmp_path, "msvd-qa-oe"), False, True)
+    assert isinstance(ev.model, torch.nn.parallel.DistributedDataParallel)
+    ev.load_checkpoint(str(ckpt))
+    clips, ids, mask, types = W.make_inputs(2, 3, 32, seed=1)
+    ref = torch.from_numpy(golden["e2e"]["msvd-qa-oe.logits"])
+    gt = ref.argmax(-1)
+    seen = []
+    h = ev.model.module.register_forward_hook(lambda m, i, o: seen.append(o.detach().float().cpu()))
+    ev.do_evaluation(loader((clips, ids, mask, types, gt)))
+    h.remove()
+    y = seen[0]
+    order = [int(((y[i][None] - ref).abs().amax(-1)).argmin()) for i in range(2)]  # DistributedSampler shuffles
+    assert sorted(order) == [0, 1]
+    assert (y - ref[order]).abs().max().item() < 0.12
+    assert abs(float(ev.last_metric_val) - 1.0) < 1e-6      # accuracy against the reference's own top-1: 100 %
+    assert np.isfinite(ev.last_loss)
+
+    # ---- train_ddp.py:89-130: trainer agent over the SAME module class, two sanity-check epochs = 4 DDP iterations
+    with ref_harness.reference_workdir(swin_sd):
+        model_t = E2EOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [3], 32)     # train_ddp.py:89-98 positional
+    model_t.load_state_dict(sd, strict=True)
+    tr = agents.AgentOE(model_t, 0, agent_args(tmp_path, "msvd-qa-oe", epoch=2), True, False)
+    fusion_before = {k: v.detach().clone() for k, v in tr.model.module.fusion_model.state_dict().items()}
+    swin_before = tr.model.module.video_extractor.swin.norm.weight.detach().clone()
+    big = [t.repeat((2,) + (1,) * (t.dim() - 1)) for t in (clips, ids, mask, types, gt)]
+    tr.do_sanity_check(loader(big))            # agent_base.py:243-246 -> process_data(train) -> step(is_train=True) x 2 x 2
+    assert tr.counter == 4
+    changed = [k for k, v in tr.model.module.fusion_model.state_dict().items()
+               if v.dtype.is_floating_point and not torch.equal(v, fusion_before[k])]
+    assert len(changed) > 200, len(changed)    # AdamW moved the encoder (233 parameter tensors)
+    assert torch.equal(tr.model.module.video_extractor.swin.norm.weight, swin_before)  # frozen extractors
+    assert all(torch.isfinite(p).all() for p in tr.model.module.fusion_model.parameters())
+
+    # ---- agent_base.py:194-217: save_checkpoint / load_checkpoint round trip with the reference's key set
+    tr.last_loss, tr.last_metric_val = 1.0, 0.5
+    tr.save_checkpoint(1)
+    files = os.listdir(tr.args.ckpt_dir)
+    assert len(files) == 1
+    blob = torch.load(os.path.join(tr.args.ckpt_dir, files[0]), map_location="cpu")
+    assert set(blob["model_state_dict"]) == set(sd)           # the reference's 783 keys
+    ev.load_checkpoint(os.path.join(tr.args.ckpt_dir, files[0]))
+    for (k, a), (_, b) in zip(ev.model.module.state_dict().items(), tr.model.module.state_dict().items()):
+        assert torch.equal(a, b), k
+    # the trained weights flow into the kernels' packed copies: evaluation output now differs from the seeded run
+    seen.clear()
+    h = ev.model.module.register_forward_hook(lambda m, i, o: seen.append(o.detach().float().cpu()))
+    ev.do_evaluation(loader((clips, ids, mask, types, gt)))
+    h.remove()
+    assert (seen[0] - y).abs().max().item() > 1e-4
+
+
+@needs_ref
+def test_reference_agent_mc_eval(golden, tmp_path, nccl_single_rank):
+    """configs[3]: AgentMC (hinge loss over 5 candidates, agent_mc.py:20-71) on E2EMultipleChoice, evaluation step."""
+    import lrce_b200
+
+    agents = ref_harness.import_agents()
+    lrce_b200.install()
+    from lrce.models.e2e import E2EMultipleChoice
+
+    sd = W.make_e2e_state_dict(1, 40, 3, seed=0)
+    swin_sd = {k[len("video_extractor.swin."):]: v for k, v in sd.items() if k.startswith("video_extractor.swin.")}
+    with ref_harness.reference_workdir(swin_sd):
+        model = E2EMultipleChoice(num_classes=1, text_seq_len=40, **CFG)
+    model.load_state_dict(sd, strict=True)
+    ev = agents.AgentMC(model, 0, agent_args(tmp_path, "tgif-action"), False, True)
+    clips, ids, mask, types = W.make_inputs(2, 3, 40, seed=1, n_candidates=5)
+    ref = torch.from_numpy(golden["e2e"]["tgif-action.logits"])
+    seen = []
+    h = ev.model.module.register_forward_hook(lambda m, i, o: seen.append(o.detach().float().cpu()))
+    ev.do_evaluation(loader((clips, ids, mask, types, ref.argmax(-1))))
+    h.remove()
+    y = seen[0]
+    order = [int(((y[i][None] - ref).abs().amax(-1)).argmin()) for i in range(2)]
+    assert sorted(order) == [0, 1] and (y - ref[order]).abs().max().item() < 0.12

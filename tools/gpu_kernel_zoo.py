@@ -106,6 +106,30 @@ if which in ("rows", "all"):
         ops.patch_merge_ln(x, g, b, 1e-5, N_SEG, 3, hw, hw, C)
         order.append(f"patch_merge_ln C{C}")
 
+if which == "mem":  # the memory-bound pieces north_star names (remap, LN, bias gather, patch gather, merge-LN), full size
+    clips = torch.rand(N_SEG, 5, 3, 224, 224, device=dev)
+    ops.patch_gather(clips)
+    order.append(f"patch_gather_f32 in {clips.numel() * 4 / 1e6:.0f} MB out {N_SEG * 9408 * 96 * 2 / 1e6:.0f} MB")
+    ops.patch_gather((clips * 255).to(torch.uint8))
+    order.append("patch_gather_u8")
+    for hw, C in [(56, 128), (28, 256), (14, 512)]:
+        x = rnd(N_SEG * 3 * hw * hw, C)
+        ops.window_remap(x, N_SEG, (3, hw, hw), (3, 7, 7), (0, 3, 3))
+        order.append(f"window_remap C{C}: algorithmic {2 * x.numel() * 2 / 1e6:.0f} MB")
+        g, b = torch.ones(4 * C, device=dev), torch.zeros(4 * C, device=dev)
+        ops.patch_merge_ln(x, g, b, 1e-5, N_SEG, 3, hw, hw, C)
+        order.append(f"patch_merge_ln C{C}: algorithmic {2 * x.numel() * 2 / 1e6:.0f} MB")
+    x = rnd(N_SEG * 147, 1024)
+    ops.layernorm(x, torch.ones(1024, device=dev), torch.zeros(1024, device=dev), 1e-5)
+    order.append(f"layernorm C1024: algorithmic {2 * x.numel() * 2 / 1e6:.0f} MB")
+    for heads in (4, 16, 32):
+        ops.window_bias_pack(torch.randn(2535, heads, device=dev) * 0.5)
+        order.append(f"window_bias_pack heads{heads}: table {2535 * heads * 4 / 1e3:.0f} KB -> dense {heads * 160 * 160 * 2 / 1e3:.0f} KB")
+    vf = rnd(32 * 3 * 3 * 49, 768)
+    e = lambda *s_: torch.randn(*s_, device=dev)
+    ops.video_posembed_ln(vf, e(768), e(50, 768), e(3, 768), e(3, 768), e(768), e(768), 1e-12, 32, 3, 3, 49)
+    order.append(f"video_posembed_ln: algorithmic {(vf.numel() + 32 * 3 * 150 * 768) * 2 / 1e6:.0f} MB")
+
 if which in ("enc", "all"):
     m = lrce_b200.LRCEOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [1], 32).cuda().eval()  # S=1: one recurrent step
     vf = rnd(32, 1, 3, 49, 1024)

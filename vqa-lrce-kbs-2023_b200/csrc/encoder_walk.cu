@@ -579,9 +579,8 @@ extern "C" int lrce_encoder_walk(const void* layer_table, int n_layers, const vo
   LRCE_REQUIRE(act >= 0 && act <= 2, "lrce_encoder_walk: unknown activation %d", act);
   LRCE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "lrce_encoder_walk: workspace must be 256-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  static thread_local bool configured = false;
-  static thread_local int max_grid = 0;
-  if (!configured) {
+  static thread_local uint64_t configured = 0;  // one bit per device
+  if (needs_device_setup(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(encoder_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WK_SMEM);
     int per_sm = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encoder_walk_kernel, WK_THREADS, WK_SMEM);
@@ -589,9 +588,9 @@ extern "C" int lrce_encoder_walk(const void* layer_table, int n_layers, const vo
       set_error("encoder_walk_kernel cannot be made resident (smem=%d): %s", WK_SMEM, cudaGetErrorString(e));
       return LRCE_ECUDA;
     }
-    max_grid = sm_count();  // one CTA per SM: every CTA of the cooperative grid is co-resident
-    configured = true;
+    mark_device_setup(&configured);
   }
+  const int max_grid = sm_count();  // one CTA per SM: every CTA of the cooperative grid is co-resident
   WalkParams p;
   p.layers = reinterpret_cast<const EncLayerW*>(layer_table);
   p.n_layers = n_layers;

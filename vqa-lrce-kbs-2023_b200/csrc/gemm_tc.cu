@@ -602,14 +602,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   auto kern = gemm_tc_kernel<BN, EPI, OutT, LNIN, CG>;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static thread_local uint64_t configured = 0;  // one bit per device: function attributes are per device
+  if (needs_device_setup(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return LRCE_ECUDA;
     }
-    configured = true;
+    mark_device_setup(&configured);
   }
   const int n_tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * (p.N / BN);
   int units = sm_count() / CG;

@@ -63,6 +63,21 @@ int sm_count() {
   return cached;
 }
 
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
+bool needs_device_setup(const uint64_t* mask) {
+  const int dev = current_device();
+  return dev < 0 || dev >= 64 || !((*mask >> dev) & 1ull);
+}
+void mark_device_setup(uint64_t* mask) {
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64) *mask |= 1ull << dev;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -27,6 +27,12 @@ int make_tmap_nd_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_
                       const uint32_t* box, int swizzle_bytes, int l2_promo_bytes);
 
 int sm_count();
+// id of the calling thread's current CUDA device (-1 on error)
+int current_device();
+// Per-(call site, device) one-time setup (cudaFuncSetAttribute and friends are per device): `mask` is the call site's
+// static thread_local bitmap. needs_device_setup() is true until mark_device_setup() was called for the current device.
+bool needs_device_setup(const uint64_t* mask);
+void mark_device_setup(uint64_t* mask);
 
 }  // namespace lrce
 

@@ -635,15 +635,16 @@ static int geom_3x7x7(StageGeom* g, int D, int H, int W, int sh, int sw) {
 // tensor maps of the four class boxes over qkv viewed as (channel 3C, w, h, frame*segment); cached per (pointer, geometry)
 struct WaMapEntry {
   const void* qkv;
-  int n_seg, H, W, C;
+  int dev, n_seg, H, W, C;
   WaMaps maps;
 };
 static int get_maps(const WaMaps** out, const void* qkv, int n_seg, int H, int W, int C) {
   static thread_local WaMapEntry cache[16];
   static thread_local int n_cached = 0, next = 0;
+  const int dev = current_device();  // the same virtual address can name different memory on another device
   for (int i = 0; i < n_cached; ++i) {
     const WaMapEntry& e = cache[i];
-    if (e.qkv == qkv && e.n_seg == n_seg && e.H == H && e.W == W && e.C == C) {
+    if (e.qkv == qkv && e.dev == dev && e.n_seg == n_seg && e.H == H && e.W == W && e.C == C) {
       *out = &e.maps;
       return LRCE_OK;
     }
@@ -658,7 +659,7 @@ static int get_maps(const WaMaps** out, const void* qkv, int n_seg, int H, int W
     const int rc = make_tmap_nd_bf16(&e.maps.m[k], qkv, 4, dims, strides, box, 64, 128);
     if (rc != LRCE_OK) return rc;
   }
-  e.qkv = qkv; e.n_seg = n_seg; e.H = H; e.W = W; e.C = C;
+  e.qkv = qkv; e.dev = dev; e.n_seg = n_seg; e.H = H; e.W = W; e.C = C;
   *out = &e.maps;
   next = (next + 1) % 16;
   if (n_cached < 16) ++n_cached;
@@ -674,8 +675,8 @@ extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(qkv && out && bias_dense && n_seg > 0, "lrce_window_attention_bf16: null operand");
   LRCE_REQUIRE(n_heads > 0 && C == n_heads * 32, "lrce_window_attention_bf16: head_dim must be 32 (C=%d heads=%d)", C, n_heads);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static thread_local uint64_t configured = 0;  // one bit per device
+  if (needs_device_setup(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
@@ -683,7 +684,7 @@ extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void
       set_error("cudaFuncSetAttribute(window_attention_kernel): %s", cudaGetErrorString(e));
       return LRCE_ECUDA;
     }
-    configured = true;
+    mark_device_setup(&configured);
   }
   const WaMaps* maps = nullptr;
   rc = get_maps(&maps, qkv, n_seg, H, W, C);

@@ -19,15 +19,32 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_logits(local: torch.Tensor, group=None) -> torch.Tensor:
-    """all_gather of equally shaped per-rank logits `(B_local, ...)` -> `(world * B_local, ...)`, rank-major (the order
-    `shard_range` hands clips out in). A no-op without an initialised process group."""
+def gather_logits(local: torch.Tensor, group=None, sizes: Sequence[int] = None) -> torch.Tensor:
+    """all_gather of per-rank logits `(B_rank, ...)` -> `(sum B_rank, ...)`, rank-major (the order `shard_range` hands clips
+    out in). `sizes` = the per-rank batch sizes when they are known to differ (a ragged last evaluation batch:
+    `shard_range` shards differ by one): every rank then pads to the largest shard, one `all_gather_into_tensor` moves the
+    padded blocks and the padding is trimmed. `sizes=None` means equal shards (checked cheaply: a mismatch would corrupt
+    the collective, so the sizes are exchanged once when the caller cannot vouch for them — pass `sizes` to skip that).
+    A no-op without an initialised process group."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
-    out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out
+    if sizes is None:
+        mine = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
+        allsz = torch.empty(world, device=local.device, dtype=torch.int64)
+        dist.all_gather_into_tensor(allsz, mine, group=group)
+        sizes = allsz.tolist()
+    if len(sizes) != world or sizes[dist.get_rank(group)] != local.shape[0]:
+        raise ValueError(f"gather_logits: sizes {list(sizes)} do not describe this rank's batch of {local.shape[0]}")
+    big = max(sizes)
+    block = local.contiguous()
+    if block.shape[0] != big:
+        block = torch.cat([block, block.new_zeros((big - block.shape[0],) + tuple(block.shape[1:]))])
+    out = local.new_empty((world * big,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, block, group=group)
+    if all(s == big for s in sizes):
+        return out
+    return torch.cat([out[r * big:r * big + s] for r, s in enumerate(sizes)])
 
 
 def _buckets(params: Sequence[torch.nn.Parameter], bucket_bytes: int) -> List[List[torch.nn.Parameter]]:

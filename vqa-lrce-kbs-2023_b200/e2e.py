@@ -27,6 +27,12 @@ class E2EBase(nn.Module):
             assert os.path.exists(SWIN_CKPT)
         self.text_extractor = TextExtractor(pretrained=pretrained)
         self.video_extractor = VideoExtractor(SWIN_CKPT if pretrained else None)
+        # The extractors of this path are forward-only kernels (Swin / BERT backward is "next"): freeze
+        # them explicitly, so that the reference agent's AdamW groups (agent_base.py:27-41), its L2 term
+        # (agent_base.py:103-108 skips parameters that do not require grad) and plain DDP(model) (agent_base.py:76) all
+        # skip them cleanly instead of waiting for gradients that never come. The reference fine-tunes all three groups.
+        for p in list(self.text_extractor.parameters()) + list(self.video_extractor.parameters()):
+            p.requires_grad_(False)
 
     def extract_text_features(self, texts, attention_mask, texts_type_ids):
         return self.text_extractor(texts, attention_mask, texts_type_ids)

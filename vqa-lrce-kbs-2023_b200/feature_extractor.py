@@ -88,23 +88,49 @@ class PatchEmbed3D(_Holder):
 
 class _PackedWeights:
     """bf16 / fp32 device copies of the parameters in the layout the kernels consume, rebuilt when any parameter
-    changes (optimizer step, load_state_dict, .to())."""
+    changes. A change is detected through the per-parameter tuple (storage pointer, autograd version counter): optimizer
+    steps, `load_state_dict`, `.to()` / `.cuda()` and DDP's initial broadcast all move one of the two. An update made
+    through `.data` (some EMA / weight-surgery code) bumps neither — call `module.invalidate_packed()` after such an
+    update. `_apply` (device / dtype moves) and `load_state_dict` invalidate explicitly as well."""
 
     def __init__(self):
         self.sig = None
         self.data = None
+        self.params = None
 
-    @staticmethod
-    def signature(module):
-        s = 0
-        dev = None
-        for p in module.parameters():
-            s += p._version + (p.data_ptr() & 0xFFFF)
-            dev = p.device
-        return (s, dev)
+    def invalidate(self):
+        self.sig = None
+        self.params = None
+
+    def signature(self, module):
+        if self.params is None:
+            self.params = list(module.parameters())
+        return tuple((p.data_ptr(), p._version) for p in self.params)
 
 
-class SwinTransformer3D(nn.Module):
+class _PackedModule(nn.Module):
+    """nn.Module with a `_packed` cache of kernel-layout weights (see _PackedWeights)"""
+
+    def invalidate_packed(self):
+        """drop the packed bf16 copies (needed only after parameter updates made through `.data`)"""
+        self._packed.invalidate()
+        for m in self.children():
+            if isinstance(m, _PackedModule):
+                m.invalidate_packed()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if "_packed" in self.__dict__:
+            self._packed.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._packed.invalidate()
+        return out
+
+
+class SwinTransformer3D(_PackedModule):
     """Video Swin backbone with the reference's constructor arguments used by VideoExtractor (video.py:10-18).
     forward: clips fp32 (n, T, 3, H, W) in [0,1] (un-normalised, frames-major as the dataset yields them) ->
     features (n, D, H/32, W/32, 8*embed) bf16 channels-last, final LayerNorm applied (video_swin_ori.py:674-687)."""
@@ -139,7 +165,7 @@ class SwinTransformer3D(nn.Module):
 
     # ---------------------------------------------------------------------------------------------------------
     def packed(self):
-        sig = _PackedWeights.signature(self)
+        sig = self._packed.signature(self)
         if self._packed.sig != sig:
             self._packed.data = self._pack()
             self._packed.sig = sig

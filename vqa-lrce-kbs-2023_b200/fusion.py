@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .feature_extractor import _PackedWeights
+from .feature_extractor import _PackedModule, _PackedWeights
 
 EPS = 1e-12  # fusionv3.py:14,18 ; embedding.py:15,45
 
@@ -63,7 +63,7 @@ class FusionTransformer(nn.Module):
         self.summarization_token = init_weight((1, 1, feature_dim))
 
 
-class LRCEOpenEnded(nn.Module):
+class LRCEOpenEnded(_PackedModule):
     KIND = "oe"
 
     def __init__(self, feature_dim: int, num_classes: int, drop_out_rate: float = 0.1,
@@ -86,7 +86,7 @@ class LRCEOpenEnded(nn.Module):
 
     # -------------------------------------------------------------------------------------------------------------
     def packed(self):
-        sig = _PackedWeights.signature(self)
+        sig = self._packed.signature(self)
         if self._packed.sig != sig:
             self._packed.data = self._pack()
             self._packed.sig = sig
@@ -146,9 +146,24 @@ class LRCEOpenEnded(nn.Module):
     def _encode(self, video_features, text_features, n_cand, act=ops.ACT_NONE, taps=None):
         """video_features (B, S, T, P, Dv) bf16; text_features (B*n_cand, L, 768) bf16/fp32 -> (B*n_cand, classes)."""
         pk = self.packed()
+        if video_features.dim() != 5 or text_features.dim() != 3:
+            raise ops._lib.LrceError(f"expected video features (B, S, T, P, Dv) and text features (B, L, 768), got "
+                                     f"{tuple(video_features.shape)} / {tuple(text_features.shape)}")
         B, S, T, P, Dv = video_features.shape
         Bq, L, d = text_features.shape
         dev = video_features.device
+        # the pos-embed kernels index emb_clip[s], emb_len[t], emb_pos[p] / emb_pos[l] directly: a dataset / model mismatch in
+        # temporal_scale, frame_sample_size, video_feature_res or text_seq_len must fail here, as the reference's broadcast
+        # adds do (embedding.py:21, :55-57), not read out of bounds
+        ve, te = self.video_pos_embed, self.question_pos_embed
+        if (S != ve.emb_clip.shape[1] or T != ve.emb_len.shape[2] or P + 1 != ve.emb_pos.shape[3]
+                or L + 1 != te.emb_pos.shape[1] or d != self.feature_dim or Dv != self.video_feature_dim
+                or Bq != B * n_cand):
+            raise ops._lib.LrceError(
+                f"shape mismatch with the embedding tables: video (B={B}, S={S}, T={T}, P={P}, Dv={Dv}) vs emb_clip rows "
+                f"{ve.emb_clip.shape[1]}, emb_len rows {ve.emb_len.shape[2]}, emb_pos rows {ve.emb_pos.shape[3]}, feature dim "
+                f"{self.video_feature_dim}; text (rows={Bq}, L={L}, d={d}) vs emb_pos rows {te.emb_pos.shape[1]}, "
+                f"{n_cand} candidate(s) per clip")
         vf = video_features.reshape(B * S * T * P, Dv)
         if vf.dtype != torch.bfloat16:
             raise ops._lib.LrceError(f"video features must be bf16 (the Swin kernels emit bf16), got {vf.dtype}")

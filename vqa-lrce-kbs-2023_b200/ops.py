@@ -26,6 +26,10 @@ def _req(t, dtype, name):
         return
     if not t.is_cuda:
         raise _lib.LrceError(f"{name} must be a CUDA tensor: the LRCE hot path has no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the current device's current stream; a tensor of another GPU would be dereferenced there
+        raise _lib.LrceError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                             "wrap the call in torch.cuda.device(...)")
     if t.dtype != dtype:
         raise _lib.LrceError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous() and t.dim() != 2:

@@ -83,22 +83,21 @@ def test_msvd_b32_batch_invariance(golden, msvd):
 
 
 def test_training_step_matches_inference_path_and_has_grads():
-    """BASELINE config 5 (tgif-frameqa training step): with dropout off, the differentiable encoder path must reproduce
-    the kernel path's logits (same algorithm, bf16 both), and backward must reach every encoder parameter and nothing
-    else."""
+    """BASELINE config 5 (tgif-frameqa training step): with dropout off, the differentiable encoder path (hand-written
+    training kernels behind one autograd node, train.py) must reproduce the inference kernels' logits, and backward must
+    reach every encoder parameter and nothing else."""
     import lrce_b200
 
     m = lrce_b200.E2EOpenEnded(num_classes=1000, text_seq_len=30, drop_out_rate=0.0, pretrained=False, **CFG)
     m.load_state_dict(W.make_e2e_state_dict(1000, 30, 3, seed=0), strict=True)
     m = m.cuda().train()
-    m.text_extractor.eval()  # HF BERT's own dropout would decorrelate the two passes being compared
     clips, ids, mask, types = W.make_inputs(2, 3, 30, seed=1)
     args = (clips.cuda(), ids.cuda(), mask.cuda(), types.cuda())
     with torch.no_grad():
         y_kernel = m(*args)
     y = m(*args)
     assert y.requires_grad and y.shape == y_kernel.shape
-    assert (y - y_kernel).abs().max().item() < 0.25, (y - y_kernel).abs().max().item()
+    assert (y - y_kernel).abs().max().item() < 0.1, (y - y_kernel).abs().max().item()
     loss = torch.nn.functional.cross_entropy(y, torch.tensor([3, 7], device="cuda"))
     loss.backward()
     enc = list(m.fusion_model.parameters())
@@ -106,25 +105,43 @@ def test_training_step_matches_inference_path_and_has_grads():
     assert sum(p.grad.abs().sum().item() for p in enc) > 0
     assert all(p.grad is None for p in m.video_extractor.parameters())
     assert all(p.grad is None for p in m.text_extractor.parameters())
+    # dropout on: a different mask every call, same expectation, finite gradients
+    m2 = lrce_b200.LRCEOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [3], 30)
+    m2.load_state_dict(W.make_fusion_state_dict(1000, 30, 3, seed=0), strict=True)
+    m2 = m2.cuda().train()
+    g = torch.Generator().manual_seed(5)
+    vf = torch.randn((2, 3, 3, 49, 1024), generator=g).bfloat16().cuda()
+    tf = torch.randn((2, 30, 768), generator=g).cuda()
+    ya, yb = m2(vf, tf), m2(vf, tf)
+    assert not torch.equal(ya, yb) and (ya - yb).abs().max().item() < 5.0
+    ya.logsumexp(-1).sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m2.parameters())
 
 
-def test_text_extractor_graph_replay_equals_eager(msvd, monkeypatch):
-    """The CUDA-graph replay of BERT (inference) must return what the eager module returns, for fresh inputs of the captured
-    shape, for a second shape, and after an in-place weight update (the graph reads the live parameters)."""
+def test_text_extractor_native_bert(golden, msvd, monkeypatch):
+    """BERT-base on liblrce_b200: against the reference's text features (golden, fp32 CPU), against the
+    HuggingFace module on the same GPU, and CUDA-graph replay == direct launches (fresh inputs, second shape, weight update)."""
     te = msvd.text_extractor
-    _, ids, mask, types = W.make_inputs(2, 3, 32, seed=5)
+    _, ids, mask, types = W.make_inputs(2, 3, 32, seed=1)
     ids, mask, types = ids.cuda(), mask.cuda(), types.cuda()
+    ref = torch.from_numpy(golden["e2e_r2"]["msvd-qa-oe.text_features"])
     with torch.no_grad():
         a = te(ids, mask, types)                      # capture + replay
+        assert a.dtype == torch.float32 and a.shape == (2, 32, 768)
+        err = rel_l2(a, ref)
+        err_hf = rel_l2(te.hf_forward(ids, mask, types), ref)
+        print(f"BERT text features vs reference: native rel-L2 {err:.3e} (HF bf16 autocast on the same GPU: {err_hf:.3e})")
+        assert err < 1e-2, err
         ids2 = torch.roll(ids, 1, dims=0)
         b = te(ids2, mask, types)                     # replay with new inputs
         monkeypatch.setenv("LRCE_B200_BERT_GRAPH", "0")
         a_ref, b_ref = te(ids, mask, types), te(ids2, mask, types)
         monkeypatch.setenv("LRCE_B200_BERT_GRAPH", "1")
-        assert not te._graph_failed and len(te._graphs) >= 1
+        assert len(te._graphs) >= 1
         assert torch.equal(a, a_ref) and torch.equal(b, b_ref)
         c = te(ids[:1], mask[:1], types[:1])          # another shape: its own graph
-        assert torch.equal(c, a_ref[:1]) or (c - a_ref[:1]).abs().max().item() < 2e-2  # batch-1 GEMMs may pick other kernels
+        assert (c - a_ref[:1]).abs().max().item() < 2e-2
+        # a parameter update re-packs the bf16 weights and re-captures
         w = te.bert.embeddings.word_embeddings.weight
         old = w.detach().clone()
         w.mul_(1.5)
@@ -133,18 +150,12 @@ def test_text_extractor_graph_replay_equals_eager(msvd, monkeypatch):
         d_ref = te(ids, mask, types)
         w.copy_(old)
         assert torch.equal(d, d_ref) and not torch.equal(d, a)
-        # capture under the agent's ambient fp16 autocast (agent_oe.py:28), replay outside of it: the graph must not hold on
-        # to autocast's cached weight copies, which die with the ambient context
         monkeypatch.setenv("LRCE_B200_BERT_GRAPH", "1")
-        ids3, mask3, types3 = (t.repeat(2, 1)[:3].contiguous() for t in (ids, mask, types))
-        with torch.autocast("cuda", dtype=torch.float16):
-            e1 = te(ids3, mask3, types3)
-        torch.cuda.empty_cache()
-        junk = torch.randn(64, 1024, 1024, device="cuda")  # recycle whatever the ambient context released
-        e2 = te(ids3, mask3, types3)
-        del junk
-        assert torch.equal(e1, e2)
-        assert (e2[:2] - a_ref).abs().max().item() < 2e-2
+        # padding is really excluded: changing the ids behind the mask must not change the attended positions' features
+        ids3 = ids.clone()
+        ids3[:, 25:] = 1234
+        e = te(ids3, mask, types)
+        assert (e[:, :20] - a[:, :20]).abs().max().item() < 1e-5
 
 
 def test_prefetch_feed_ring_delivers_every_batch():

@@ -125,3 +125,58 @@ def test_posembed_rejects_mismatched_shapes():
                              (vf, (1, 33, 768)), (vf, (1, 31, 768))):
             with pytest.raises(lrce_b200.LrceError):
                 m(bad_v.contiguous(), torch.zeros(bad_t, device="cuda"), None)
+
+
+def test_training_step_gradients_vs_reference(golden):
+    """BASELINE configs[4]: gradients of the cross-entropy loss w.r.t. every encoder parameter from the hand-written
+    forward + backward kernels (train.py) against the reference LRCEOpenEnded with drop_out_rate=0 (fp32 CPU autograd,
+    oracle/make_golden.py golden_grad). bf16 operands / fp32 accumulation: per-parameter norms within 4 %, sampled entries
+    within 6 % of the parameter's largest sampled gradient, loss within 2e-2."""
+    import lrce_b200
+
+    g = golden["grad"]
+    m = lrce_b200.LRCEOpenEnded(768, 1000, 0.0, [7, 7], 1024, 5, [3], 30)
+    m.load_state_dict(W.make_fusion_state_dict(1000, 30, 3, seed=0), strict=True)
+    m = m.cuda().train()
+    vf, tf = seeded((4, 3, 3, 49, 1024), 320), seeded((4, 30, 768), 321)
+    y = m(vf.bfloat16().cuda(), tf.cuda(), None)
+    loss = torch.nn.functional.cross_entropy(y, torch.from_numpy(g["target"]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    print("train fwd: logits max-abs", (y.detach().cpu() - torch.from_numpy(g["logits"])).abs().max().item(),
+          "loss", loss.item(), "ref", float(g["loss"][0]))
+    assert abs(loss.item() - float(g["loss"][0])) < 5e-2
+    params = dict(m.named_parameters())
+    worst_norm, worst_samp, worst = 0.0, 0.0, None
+    tot_ref = float(np.sqrt((g["norms"] ** 2).sum()))
+    sq = 0.0
+    for name, norm in zip(g["names"].tolist(), g["norms"].tolist()):
+        gr = params[name].grad
+        assert gr is not None and torch.isfinite(gr).all(), name
+        gr = gr.float().cpu()
+        ref = torch.from_numpy(g["g." + name])
+        samp = gr.reshape(-1)[::1999]
+        scale = max(ref.abs().max().item(), 1e-3 * tot_ref / 233 ** 0.5)
+        e_s = (samp - ref).abs().max().item() / scale
+        e_n = abs(gr.double().norm().item() - norm) / max(norm, 1e-3 * tot_ref / 233 ** 0.5)
+        sq += ((samp - ref) ** 2).sum().item()
+        if max(e_s, e_n) > max(worst_norm, worst_samp):
+            worst = name
+        worst_norm, worst_samp = max(worst_norm, e_n), max(worst_samp, e_s)
+        assert e_n < 0.04 and e_s < 0.06, (name, e_n, e_s)
+    print(f"gradient parity over 233 tensors: worst norm error {worst_norm:.3e}, worst sampled-entry error {worst_samp:.3e} ({worst})")
+
+
+def test_bert_mc_shape_vs_reference(golden):
+    """the multiple-choice text shape (5 candidates x L = 40 -> 10 sequences): native BERT features vs the reference sample"""
+    import lrce_b200
+
+    te = lrce_b200.TextExtractor(pretrained=False)
+    te.bert.load_state_dict(W.make_bert_state_dict(seed=0), strict=True)
+    te = te.cuda().eval()
+    _, ids, mask, types = W.make_inputs(2, 3, 40, seed=3, n_candidates=5)
+    with torch.no_grad():
+        t = te(ids.flatten(0, 1).cuda(), mask.flatten(0, 1).cuda(), types.flatten(0, 1).cuda())
+    err = rel_l2(t.reshape(-1)[::997], torch.from_numpy(golden["e2e_r2"]["tgif-transition.text_features.sample"]))
+    print("BERT MC-shape features rel-L2", err)
+    assert err < 1e-2, err

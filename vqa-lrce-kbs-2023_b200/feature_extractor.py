@@ -295,14 +295,26 @@ class VideoExtractor(nn.Module):
         return f.view(B, S, f.shape[1], f.shape[2] * f.shape[3], f.shape[4])
 
 
-class TextExtractor(nn.Module):
-    """lrce.feature_extractor.text.TextExtractor (text.py:5-17): HF BertModel, unchanged PyTorch.
-    Runs under bf16 autocast regardless of the ambient autocast dtype.
+class TextExtractor(_PackedModule):
+    """lrce.feature_extractor.text.TextExtractor (text.py:5-17): BERT-base, `forward(input_ids, attention_mask,
+    token_type_ids) -> last_hidden_state (B, L, 768)` fp32. The HuggingFace `BertModel` is kept as the PARAMETER CONTAINER
+    (identical `state_dict` keys: `text_extractor.bert.*`), but the forward pass runs on liblrce_b200:
 
-    BERT-base on one batch of questions is ~400 short library kernels: launch-bound (5 ms of host time for < 1 ms of
-    device work). In inference (no grad) the forward is therefore captured once per input shape into a CUDA graph and
-    replayed; the graph reads the live parameters, so weight updates / `load_state_dict` need no re-capture. Set
-    LRCE_B200_BERT_GRAPH=0 to run the module eagerly."""
+      embeddings   lrce_bert_embed_ln        LayerNorm(word[ids] + position[0..L) + token_type[type_ids]), eps 1e-12
+      per layer    lrce_gemm_bf16            fused q|k|v projection  [n, 768] x [2304, 768]^T
+                   lrce_bert_attention       12 heads x 64, keys with attention_mask == 0 excluded (HF adds finfo.min)
+                   lrce_gemm_bf16 (fp32 out) attention.output.dense
+                   lrce_add_ln_768           LayerNorm(dense + residual), fp32 residual stream + bf16 copy for the next GEMM
+                   lrce_gemm_bf16 (GELU)     intermediate.dense + erf-GELU
+                   lrce_gemm_bf16 (fp32 out) output.dense
+                   lrce_add_ln_768           LayerNorm(dense + residual)
+      the pooler is never evaluated (text.py:17 returns last_hidden_state only).
+
+    ~86 short launches per batch of questions: launch-bound, so in inference the sequence is captured once per input shape
+    into a CUDA graph and replayed (the graph reads the packed bf16 weights, which are re-captured when a parameter
+    changes). LRCE_B200_BERT_GRAPH=0 launches the kernels directly. BERT is forward-only on this path (its parameters are
+    frozen by E2EBase): `hf_forward` (the unchanged HuggingFace module under bf16 autocast) exists for the parity tests only
+    and is not used by `forward`."""
 
     def __init__(self, pretrained=True):
         super().__init__()
@@ -312,75 +324,122 @@ class TextExtractor(nn.Module):
             self.bert = transformers.BertModel.from_pretrained("bert-base-uncased")
         else:
             self.bert = transformers.BertModel(transformers.BertConfig())
-        self._graphs = {}  # (shape, device, param identity) -> (graph, static inputs, static output); never pickled
-        self._graph_failed = False
+        cfg = self.bert.config
+        if (cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size, cfg.hidden_act) != (768, 12, 3072, "gelu"):
+            raise ops._lib.LrceError("liblrce_b200's BERT kernels are specialised for bert-base (768 / 12 heads / 3072 / gelu)")
+        self._packed = _PackedWeights()
+        self._graphs = {}  # (shape, device, packed-weights identity) -> (graph, static inputs, static output); never pickled
 
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_graphs"] = {}
+        state["_packed"] = _PackedWeights()
         return state
 
     def __deepcopy__(self, memo):
         import copy
 
-        graphs, self._graphs = self._graphs, {}
+        graphs, packed = self._graphs, self._packed
+        self._graphs, self._packed = {}, _PackedWeights()
         try:
             cls = self.__class__
             new = cls.__new__(cls)
             memo[id(self)] = new
             new.__dict__ = copy.deepcopy(self.__dict__, memo)
         finally:
-            self._graphs = graphs
+            self._graphs, self._packed = graphs, packed
         return new
 
-    def _eager(self, input_ids, attention_mask, token_type_ids):
-        # cache_enabled=False: under an ambient autocast (the reference's agents wrap the model call in one, agent_oe.py:28)
-        # the weight-cast cache outlives this context; a graph captured then would reference cached bf16 copies that are
-        # freed when the ambient context exits. Without the cache every cast is a node of the graph reading the live weights.
+    # ---------------------------------------------------------------------------------------------------------
+    def packed(self):
+        sig = self._packed.signature(self)
+        if self._packed.sig != sig:
+            self._packed.data = self._pack()
+            self._packed.sig = sig
+            self._graphs = {}  # graphs hold pointers into the old packed copies
+        return self._packed.data
+
+    @torch.no_grad()
+    def _pack(self):
+        emb, enc = self.bert.embeddings, self.bert.encoder
+        dev = emb.word_embeddings.weight.device
+        if dev.type != "cuda":
+            raise ops._lib.LrceError("TextExtractor parameters must live on a CUDA device (no CPU fallback)")
+        bf = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        pk = dict(word=f32(emb.word_embeddings.weight), pos=f32(emb.position_embeddings.weight),
+                  type=f32(emb.token_type_embeddings.weight), eg=f32(emb.LayerNorm.weight), eb=f32(emb.LayerNorm.bias),
+                  eps=float(self.bert.config.layer_norm_eps), layers=[])
+        for lyr in enc.layer:
+            sa, so = lyr.attention.self, lyr.attention.output
+            pk["layers"].append(dict(
+                wqkv=bf(torch.cat([sa.query.weight, sa.key.weight, sa.value.weight])),
+                bqkv=f32(torch.cat([sa.query.bias, sa.key.bias, sa.value.bias])),
+                wo=bf(so.dense.weight), bo=f32(so.dense.bias), g1=f32(so.LayerNorm.weight), b1=f32(so.LayerNorm.bias),
+                w1=bf(lyr.intermediate.dense.weight), bi=f32(lyr.intermediate.dense.bias),
+                w2=bf(lyr.output.dense.weight), bo2=f32(lyr.output.dense.bias),
+                g2=f32(lyr.output.LayerNorm.weight), b2=f32(lyr.output.LayerNorm.bias)))
+        return pk
+
+    def _native(self, input_ids, attention_mask, token_type_ids):
+        pk = self.packed()
+        if input_ids.dim() != 2:
+            raise ops._lib.LrceError(f"expected input_ids (B, L), got {tuple(input_ids.shape)}")
+        B, L = input_ids.shape
+        ids = input_ids.contiguous()
+        mask = None if attention_mask is None else attention_mask.to(torch.int64).contiguous()
+        types = None if token_type_ids is None else token_type_ids.to(torch.int64).contiguous()
+        eps = pk["eps"]
+        x32, xb = ops.bert_embed_ln(ids, types, pk["word"], pk["pos"], pk["type"], pk["eg"], pk["eb"], eps)
+        h32, hb = torch.empty_like(x32), torch.empty_like(xb)
+        for lw in pk["layers"]:
+            qkv = ops.gemm(xb, lw["wqkv"], lw["bqkv"])
+            att = ops.bert_attention(qkv, mask, B, L)
+            o = ops.gemm(att, lw["wo"], lw["bo"], out_fp32=True)
+            ops.add_ln(o, x32, lw["g1"], lw["b1"], eps, y_f32=h32, y_bf16=hb)
+            f = ops.gemm(hb, lw["w1"], lw["bi"], epilogue=ops.EPI_BIAS_GELU)
+            y = ops.gemm(f, lw["w2"], lw["bo2"], out_fp32=True)
+            ops.add_ln(y, h32, lw["g2"], lw["b2"], eps, y_f32=x32, y_bf16=xb)
+        return x32.view(B, L, 768)
+
+    def hf_forward(self, input_ids, attention_mask, token_type_ids):
+        """the unchanged HuggingFace module under bf16 autocast: parity tests only (library kernels), never on the product path"""
         with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
             return self.bert(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids,
                              output_hidden_states=False).last_hidden_state
 
-    def _param_key(self):
-        p = next(self.bert.parameters())
-        return (p.data_ptr(), p.dtype, self.bert.training)
-
     def forward(self, input_ids, attention_mask, token_type_ids):
-        use_graph = (input_ids.is_cuda and not torch.is_grad_enabled() and not self.bert.training
-                     and not self._graph_failed and os.environ.get("LRCE_B200_BERT_GRAPH", "1") != "0"
-                     and not torch.cuda.is_current_stream_capturing())
+        if not input_ids.is_cuda:
+            raise ops._lib.LrceError("TextExtractor needs CUDA inputs on a B200: the hot path has no CPU fallback")
+        pk = self.packed()  # (re)pack outside any capture
+        use_graph = (not torch.is_grad_enabled() and os.environ.get("LRCE_B200_BERT_GRAPH", "1") != "0"
+                     and ops.trace is None and not torch.cuda.is_current_stream_capturing())
         if not use_graph:
-            return self._eager(input_ids, attention_mask, token_type_ids)
-        key = (tuple(input_ids.shape), input_ids.dtype, attention_mask.dtype, token_type_ids.dtype, input_ids.device,
-               self._param_key())
+            with torch.no_grad():
+                return self._native(input_ids, attention_mask, token_type_ids)
+        key = (tuple(input_ids.shape), attention_mask is None, token_type_ids is None, input_ids.device, id(pk))
         entry = self._graphs.get(key)
         if entry is None:
             if len(self._graphs) >= 8:  # shapes are few in practice (one per dataset config); drop the oldest
                 self._graphs.pop(next(iter(self._graphs)))
-            static_in = [input_ids.clone(), attention_mask.clone(), token_type_ids.clone()]
+            static_in = [None if t is None else t.to(torch.int64).clone() for t in (input_ids, attention_mask, token_type_ids)]
             cur = torch.cuda.current_stream(input_ids.device)
             warm = torch.cuda.Stream(device=input_ids.device)
             warm.wait_stream(cur)
-            with torch.cuda.stream(warm):  # library warm-up (lazy handles, autotune) outside the capture
-                for _ in range(2):
-                    self._eager(*static_in)
+            with torch.cuda.stream(warm):  # one-time kernel attribute setup / allocator warm-up outside the capture
+                self._native(*static_in)
             cur.wait_stream(warm)
             graph = torch.cuda.CUDAGraph()
-            try:
-                # thread_local: other threads of the process (NCCL's watchdog, a DataLoader pin-memory thread) may issue CUDA
-                # calls while this thread captures
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                    static_out = self._eager(*static_in)
-            except Exception as e:  # a library op that cannot be captured: stay eager from now on (still the same math)
-                self._graph_failed = True
-                import warnings
-
-                warnings.warn(f"lrce_b200: BERT CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
-                torch.cuda.synchronize(input_ids.device)
-                return self._eager(input_ids, attention_mask, token_type_ids)
-            entry = self._graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
+            launches0 = ops.launches
+            # thread_local: other threads of the process (NCCL's watchdog, a DataLoader pin-memory thread) may issue CUDA
+            # calls while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                static_out = self._native(*static_in)
+            entry = self._graphs[key] = (graph, static_in, static_out, ops.launches - launches0)
+        graph, static_in, static_out, n_launches = entry
         for dst, src in zip(static_in, (input_ids, attention_mask, token_type_ids)):
-            dst.copy_(src, non_blocking=True)
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
         graph.replay()  # on the caller's current stream (the E2E module's side stream)
+        ops.launches += n_launches  # kernels of this library launched by the replay
         return static_out.clone()  # the static output is rewritten by the next replay

@@ -142,16 +142,12 @@ class LRCEOpenEnded(_PackedModule):
         pk["layer_table"] = torch.tensor(rows, dtype=torch.int64, device=dev)
         return pk
 
-    # -------------------------------------------------------------------------------------------------------------
-    def _encode(self, video_features, text_features, n_cand, act=ops.ACT_NONE, taps=None):
-        """video_features (B, S, T, P, Dv) bf16; text_features (B*n_cand, L, 768) bf16/fp32 -> (B*n_cand, classes)."""
-        pk = self.packed()
+    def _validate(self, video_features, text_features, n_cand):
         if video_features.dim() != 5 or text_features.dim() != 3:
             raise ops._lib.LrceError(f"expected video features (B, S, T, P, Dv) and text features (B, L, 768), got "
                                      f"{tuple(video_features.shape)} / {tuple(text_features.shape)}")
         B, S, T, P, Dv = video_features.shape
         Bq, L, d = text_features.shape
-        dev = video_features.device
         # the pos-embed kernels index emb_clip[s], emb_len[t], emb_pos[p] / emb_pos[l] directly: a dataset / model mismatch in
         # temporal_scale, frame_sample_size, video_feature_res or text_seq_len must fail here, as the reference's broadcast
         # adds do (embedding.py:21, :55-57), not read out of bounds
@@ -164,6 +160,15 @@ class LRCEOpenEnded(_PackedModule):
                 f"{ve.emb_clip.shape[1]}, emb_len rows {ve.emb_len.shape[2]}, emb_pos rows {ve.emb_pos.shape[3]}, feature dim "
                 f"{self.video_feature_dim}; text (rows={Bq}, L={L}, d={d}) vs emb_pos rows {te.emb_pos.shape[1]}, "
                 f"{n_cand} candidate(s) per clip")
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _encode(self, video_features, text_features, n_cand, act=ops.ACT_NONE, taps=None):
+        """video_features (B, S, T, P, Dv) bf16; text_features (B*n_cand, L, 768) bf16/fp32 -> (B*n_cand, classes)."""
+        pk = self.packed()
+        self._validate(video_features, text_features, n_cand)
+        B, S, T, P, Dv = video_features.shape
+        Bq, L, d = text_features.shape
+        dev = video_features.device
         vf = video_features.reshape(B * S * T * P, Dv)
         if vf.dtype != torch.bfloat16:
             raise ops._lib.LrceError(f"video features must be bf16 (the Swin kernels emit bf16), got {vf.dtype}")
@@ -204,42 +209,30 @@ class LRCEOpenEnded(_PackedModule):
     def _wants_grad(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def _encode_autograd(self, video_features, text_features, n_cand, act=ops.ACT_NONE):
-        """Training step of the encoder (BASELINE.json config 5): the same algorithm expressed on the module's own
-        parameters with differentiable PyTorch library ops under bf16 autocast, so that autograd provides the backward
-        pass (hand-written backward kernels are not built yet — DESIGN.md §7). Dropout is active in train() mode, as in
-        the reference (fusionv3.py:190-191, :49). The extractors feeding it stay on liblrce_b200 and are not
-        differentiated through. video_features (B, S, T, P, Dv); text_features (B*n_cand, L, 768)."""
-        ve, te, ft = self.video_pos_embed, self.question_pos_embed, self.fusion_transformer
-        B, S, T, P, _ = video_features.shape
-        Bq = text_features.shape[0]
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            v = video_features.float()
-            if hasattr(self, "projection_layer"):
-                v = self.projection_layer(v)  # fusionv3.py:184-185
-            # VideoPosEmbed (embedding.py:47-63): CLS per frame, position / frame-index / segment embeddings, LayerNorm
-            v = torch.cat([ve.emb_cls.expand(B, S, T, -1, -1), v], dim=3)
-            v = ve.layer_norm(v + ve.emb_pos + ve.emb_len + ve.emb_clip).view(B, S, T * (P + 1), -1)
-            # TextPosEmbed (embedding.py:17-23)
-            t = torch.cat([te.emb_cls.expand(Bq, -1, -1), text_features.float()], dim=1)
-            t = te.layer_norm(t + te.emb_pos)
-            v, t = self.video_dropout(v), self.question_dropout(t)
-            if n_cand > 1:  # fusionv3.py:259: every candidate attends the same clip
-                v = v.unsqueeze(1).expand(-1, n_cand, -1, -1, -1).flatten(0, 1)
-            tok = ft.summarization_token.expand(Bq, -1, -1)
-            for s in range(S):  # fusionv3.py:41-49
-                mem = torch.cat([v[:, s], t], dim=1)
-                tok = ft.dropout(ft.fusion_layer_norm(tok + ft.transformer(tok, mem)))
-            out = self.final_fc(tok.squeeze(1))
-        out = out.float()
-        return torch.relu(out) if act == ops.ACT_RELU else out
+    def _train_pack(self):
+        """bf16 operands of the training step (train.pack_train), rebuilt when a parameter changed"""
+        sig = self._packed.signature(self)
+        if getattr(self, "_tpack_sig", None) != sig:
+            from . import train
+
+            self._tpack, self._tpack_sig = train.pack_train(self), sig
+        return self._tpack
+
+    def _encode_train(self, video_features, text_features, n_cand, act=ops.ACT_NONE):
+        """differentiable forward (grad enabled): the hand-written training kernels behind one autograd node (train.py);
+        `grad_sync = "overlap"` on this module additionally all-reduces the gradients inside the backward pass."""
+        from . import train
+
+        self._validate(video_features, text_features, n_cand)
+        out = train.encoder_train(self, video_features, text_features, n_cand)
+        return torch.relu(out) if act == ops.ACT_RELU else out  # LRCECount's ReLU (fusionv3.py:368) on a (B,) vector
 
     def forward(self, video_features, text_features, texts_attention_mask=None, taps=None):
         """(B, S, T, 49, Dv), (B, L, 768) -> (B, num_classes) fp32 (fusionv3.py:168-198). `texts_attention_mask` is
         accepted and ignored, exactly like the reference (fusionv3.py:31)."""
         B = video_features.shape[0]
         if self._wants_grad() and taps is None:
-            return self._encode_autograd(video_features, text_features, 1).view(B, -1)
+            return self._encode_train(video_features, text_features, 1).view(B, -1)
         return self._encode(video_features, text_features, 1, taps=taps).view(B, -1)
 
 
@@ -255,7 +248,7 @@ class LRCEMultipleChoice(LRCEOpenEnded):
         """text_features (B, n_cand, L, 768) -> (B, n_cand) (fusionv3.py:230-265)"""
         B, n_cand = text_features.shape[:2]
         if self._wants_grad() and taps is None:
-            return self._encode_autograd(video_features, text_features.flatten(0, 1), n_cand).view(B, n_cand)
+            return self._encode_train(video_features, text_features.flatten(0, 1), n_cand).view(B, n_cand)
         return self._encode(video_features, text_features.flatten(0, 1), n_cand, taps=taps).view(B, n_cand)
 
 
@@ -271,5 +264,5 @@ class LRCECount(LRCEOpenEnded):
         """(B,) = relu(final_fc(token)) (fusionv3.py:360-369)"""
         B = video_features.shape[0]
         if self._wants_grad() and taps is None:
-            return self._encode_autograd(video_features, text_features, 1, act=ops.ACT_RELU).view(B)
+            return self._encode_train(video_features, text_features, 1, act=ops.ACT_RELU).view(B)
         return self._encode(video_features, text_features, 1, act=ops.ACT_RELU, taps=taps).view(B)

@@ -223,3 +223,140 @@ def encoder_walk(layer_table, n_layers, kv_video, kv_text, tok0, f_g, f_b, eps, 
           work=(f"R{rows}S{S}", 2.0 * rows * S * n_layers * (4 * 768 * 768 + 2 * 768 * 3072 + 2 * (Tv + Lt) * 768),
                 2.0 * S * n_layers * (3 * 768 * 768 + 2 * 768 * 3072) + 2.0 * rows * S * n_layers * (Tv + Lt) * 1536 * 2))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# row / sequence kernels (csrc/seqops.cu): BERT-base and the encoder's training step
+# ----------------------------------------------------------------------------------------------------------------------
+ROWS_CAST, ROWS_GELU_FWD, ROWS_GELU_BWD = 0, 1, 2
+XATTN_MAXK = 256
+
+
+def _t(tT):
+    """(pointer, ld, row offset) of an optional transposed-copy target given as (tensor [cols, ld], row offset)"""
+    if tT is None:
+        return 0, 0, 0
+    t, r0 = tT
+    _req(t, torch.bfloat16, "transposed copy")
+    assert t.dim() == 2 and t.stride(1) == 1
+    return t.data_ptr(), t.stride(0), int(r0)
+
+
+def add_ln(a, res, gamma, beta, eps, *, res_bcast=False, u_out=None, y_f32=None, y_bf16=None, yT=None, p_a=0.0, site_a=0,
+           p_out=0.0, site_out=0, seed=0):
+    """y = drop_out(LN(res + drop_a(a))), fp32 rows of 768 (lrce_add_ln_768)"""
+    _req(a, torch.float32, "a"); _req(res, torch.float32, "res"); _req(u_out, torch.float32, "u_out")
+    _req(y_f32, torch.float32, "y_f32"); _req(y_bf16, torch.bfloat16, "y_bf16")
+    n = (a if a is not None else (y_f32 if y_f32 is not None else y_bf16)).numel() // 768
+    tp, ld, r0 = _t(yT)
+    _call("lrce_add_ln_768", _ptr(a), _ptr(res), int(res_bcast), _ptr(gamma), _ptr(beta), float(eps), _ptr(u_out), _ptr(y_f32),
+          _ptr(y_bf16), tp, ld, r0, n, float(p_a), int(site_a), float(p_out), int(site_out), int(seed), _stream())
+
+
+def ln_bwd(dy_a, dy_b, u, gamma, eps, dgamma, dbeta, *, du=None, dub=None, dubT=None, p_a=0.0, site_a=0, p_out=0.0, site_out=0,
+           seed=0):
+    _req(dy_a, torch.float32, "dy_a"); _req(dy_b, torch.float32, "dy_b"); _req(u, torch.float32, "u")
+    _req(du, torch.float32, "du"); _req(dub, torch.bfloat16, "dub"); _req(dgamma, torch.float32, "dgamma")
+    n = u.numel() // 768
+    tp, ld, r0 = _t(dubT)
+    _call("lrce_ln_bwd_768", _ptr(dy_a), _ptr(dy_b), _ptr(u), _ptr(gamma), float(eps), _ptr(du), _ptr(dub), tp, ld, r0,
+          _ptr(dgamma), _ptr(dbeta), n, float(p_a), int(site_a), float(p_out), int(site_out), int(seed), _stream())
+
+
+def rows_to_bf16(x, *, aux=None, y=None, yT=None, mode=ROWS_CAST, group=1, p=0.0, site=0, seed=0):
+    """fp32 [n, C] -> bf16 (+ transposed copy) with optional GELU forward / backward and dropout (lrce_rows_f32_to_bf16)"""
+    _req(x, torch.float32, "x"); _req(aux, torch.float32, "aux"); _req(y, torch.bfloat16, "y")
+    assert x.is_contiguous() and x.dim() == 2
+    n, C = x.shape
+    tp, ld, r0 = _t(yT)
+    _call("lrce_rows_f32_to_bf16", _ptr(x), _ptr(aux), _ptr(y), tp, ld, r0, n, C, mode, group, float(p), int(site), int(seed),
+          _stream())
+    return y
+
+
+def dropout_bf16_(x, p, site, seed):
+    _req(x, torch.bfloat16, "x")
+    assert x.is_contiguous()
+    if p > 0:
+        _call("lrce_dropout_bf16", _ptr(x), x.numel(), float(p), int(site), int(seed), _stream())
+    return x
+
+
+def xattn_fwd(q, kv_video, kv_text, kcol, R, S, seg, Tv, Lt, n_cand, P, ctx, ctxT=None, p=0.0, site=0, seed=0):
+    _req(q, torch.float32, "q"); _req(kv_video, torch.bfloat16, "kv_video"); _req(kv_text, torch.bfloat16, "kv_text")
+    _req(P, torch.float32, "P"); _req(ctx, torch.bfloat16, "ctx")
+    assert kv_video.stride(0) == kv_text.stride(0) and P.numel() >= R * 12 * XATTN_MAXK
+    tp, ld, r0 = _t(ctxT)
+    _call("lrce_xattn_fwd", _ptr(q), _ptr(kv_video), _ptr(kv_text), kv_video.stride(0), kcol, R, S, seg, Tv, Lt, n_cand, _ptr(P),
+          _ptr(ctx), tp, ld, r0, float(p), int(site), int(seed), _stream())
+
+
+def xattn_bwd(q, kv_video, kv_text, kcol, R, S, seg, Tv, Lt, n_cand, P, dctx, dq, dkv_video, dkv_text, dqT=None, p=0.0, site=0,
+              seed=0):
+    _req(q, torch.float32, "q"); _req(dctx, torch.float32, "dctx"); _req(dq, torch.bfloat16, "dq")
+    _req(dkv_video, torch.bfloat16, "dkv_video"); _req(dkv_text, torch.bfloat16, "dkv_text")
+    assert dkv_video.stride(0) == kv_video.stride(0) == dkv_text.stride(0) == kv_text.stride(0)
+    tp, ld, r0 = _t(dqT)
+    _call("lrce_xattn_bwd", _ptr(q), _ptr(kv_video), _ptr(kv_text), kv_video.stride(0), kcol, R, S, seg, Tv, Lt, n_cand, _ptr(P),
+          _ptr(dctx), _ptr(dq), tp, ld, r0, _ptr(dkv_video), _ptr(dkv_text), float(p), int(site), int(seed), _stream())
+
+
+def rowsum_bf16(src, cols, out, accumulate=False):
+    _req(src, torch.bfloat16, "src"); _req(out, torch.float32, "out")
+    assert src.dim() == 2 and src.stride(1) == 1 and out.numel() == src.shape[0]
+    _call("lrce_rowsum_bf16", _ptr(src), src.stride(0), cols, _ptr(out), src.shape[0], int(accumulate), _stream())
+
+
+def colsum(src, out):
+    """out[c] += sum_r src[r, c] (out fp32, initialised by the caller)"""
+    assert src.dtype in (torch.float32, torch.bfloat16) and src.dim() == 2 and src.stride(1) == 1
+    _req(src, src.dtype, "src"); _req(out, torch.float32, "out")
+    _call("lrce_colsum", _ptr(src), int(src.dtype == torch.bfloat16), src.shape[0], src.shape[1], src.stride(0), _ptr(out), _stream())
+
+
+def transpose_bf16(src, dst=None):
+    _req(src, torch.bfloat16, "src")
+    assert src.dim() == 2 and src.stride(1) == 1
+    rows, cols = src.shape
+    if dst is None:
+        dst = torch.empty((cols, (rows + 7) // 8 * 8), device=src.device, dtype=torch.bfloat16)
+        if dst.shape[1] != rows:
+            dst[:, rows:].zero_()
+    _call("lrce_transpose_bf16", _ptr(src), rows, cols, src.stride(0), _ptr(dst), dst.stride(0), _stream())
+    return dst
+
+
+def add_bf16(dst, a, b, c=None):
+    _call("lrce_add_bf16", _ptr(dst), _ptr(a), _ptr(b), _ptr(c), dst.numel(), _stream())
+    return dst
+
+
+def posembed_bwd(dy, *, proj=None, text=None, emb_cls, emb_pos, emb_len=None, emb_clip=None, gamma, eps, dproj=None, d_cls, d_pos,
+                 d_len=None, d_clip=None, dgamma, dbeta, B, S, T, P, is_text, p=0.0, site=0, seed=0):
+    _req(dy, torch.float32, "dy")
+    _call("lrce_posembed_bwd", _ptr(dy), _ptr(proj), _ptr(text), int(text is not None and text.dtype == torch.float32),
+          _ptr(emb_cls), _ptr(emb_pos), _ptr(emb_len), _ptr(emb_clip), _ptr(gamma), float(eps), _ptr(dproj), _ptr(d_cls),
+          _ptr(d_pos), _ptr(d_len), _ptr(d_clip), _ptr(dgamma), _ptr(dbeta), B, S, T, P, int(is_text), float(p), int(site),
+          int(seed), _stream())
+
+
+def bert_embed_ln(ids, type_ids, word, pos, type_emb, gamma, beta, eps):
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous() and ids.dim() == 2
+    assert type_ids is None or (type_ids.dtype == torch.int64 and type_ids.is_contiguous() and type_ids.shape == ids.shape)
+    _req(word, torch.float32, "word embeddings"); _req(pos, torch.float32, "position embeddings")
+    n, L = ids.numel(), ids.shape[1]
+    out_f32 = torch.empty((n, 768), device=ids.device, dtype=torch.float32)
+    out_bf16 = torch.empty((n, 768), device=ids.device, dtype=torch.bfloat16)
+    _call("lrce_bert_embed_ln", _ptr(ids), _ptr(type_ids), _ptr(word), _ptr(pos), _ptr(type_emb), _ptr(gamma), _ptr(beta),
+          float(eps), _ptr(out_f32), _ptr(out_bf16), n, L, word.shape[0], type_emb.shape[0], pos.shape[0], _stream())
+    return out_f32, out_bf16
+
+
+def bert_attention(qkv, mask, n_seq, L, n_heads=12):
+    _req(qkv, torch.bfloat16, "qkv")
+    assert qkv.is_contiguous() and qkv.shape == (n_seq * L, 3 * 64 * n_heads)
+    assert mask is None or (mask.dtype == torch.int64 and mask.is_contiguous() and mask.shape == (n_seq, L))
+    out = torch.empty((n_seq * L, 64 * n_heads), device=qkv.device, dtype=torch.bfloat16)
+    _call("lrce_bert_attention", _ptr(qkv), _ptr(mask), _ptr(out), n_seq, L, n_heads, _stream(),
+          work=(f"L{L}", 4.0 * n_seq * n_heads * L * L * 64, 2.0 * qkv.numel() + 2.0 * out.numel()))
+    return out

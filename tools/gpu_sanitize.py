@@ -91,7 +91,7 @@ if "bert" in which and hasattr(ops, "bert_attention"):
     import weights as W
 
     te = lrce_b200.TextExtractor(pretrained=False)
-    te.bert.load_state_dict(W.make_bert_state_dict(seed=0), strict=True)
+    te.bert.load_state_dict(W.make_bert_state_dict(seed=0), strict=True)  # any weights do here
     te = te.cuda().eval()
     _, ids, mask, types = W.make_inputs(2, 1, 32, seed=1)
     with torch.no_grad():

@@ -496,8 +496,10 @@ def run_b200_arm(args):
 # ----------------------------------------------------------------------------------------------------------------------
 def run_train_arm(args):
     """BASELINE.json configs[4]: TGIF-FrameQA training step, clip-sharded data parallel: extractors forward-only on
-    liblrce_b200, cross-modal encoder forward + backward (PyTorch autograd, bf16 autocast), bucketed NCCL all-reduce of the
-    115 M encoder gradients, AdamW step on the encoder. Not the headline metric; printed as its own JSON line."""
+    liblrce_b200, cross-modal encoder forward + backward on the hand-written training kernels (lrce_b200/train.py), the
+    115 M encoder gradients all-reduced over NCCL layer by layer INSIDE the backward pass (`grad_sync = "overlap"`), AdamW
+    step on the encoder (torch's fused optimizer, as the reference agent uses torch's AdamW). Not the headline metric;
+    printed as its own JSON line."""
     import torch
     import torch.distributed as dist
 
@@ -518,9 +520,7 @@ def run_train_arm(args):
     cls = {"oe": lrce_b200.E2EOpenEnded, "mc": lrce_b200.E2EMultipleChoice, "count": lrce_b200.E2ECount}[cfg["kind"]]
     torch.manual_seed(0)
     model = cls(pretrained=False, **model_kwargs(cfg)).to(dev).train()
-    model.text_extractor.eval()
-    for p in list(model.video_extractor.parameters()) + list(model.text_extractor.parameters()):
-        p.requires_grad_(False)
+    model.fusion_model.grad_sync = "overlap"  # all-reduce each layer's gradients as soon as the backward pass completes them
     enc = [p for p in model.fusion_model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(enc, lr=1e-5, fused=True)
     B = args.batch
@@ -535,14 +535,13 @@ def run_train_arm(args):
     else:
         target = torch.randint(1, 10, (B,), generator=g).float().to(dev)
         loss_fn = torch.nn.functional.mse_loss
-    grad_bytes = [0]
+    grad_bytes = [sum(p.numel() * 4 for p in enc)]
 
     def step():
         inputs = [t.to(dev, non_blocking=True) for t in host]
         loss = loss_fn(model(*inputs), target)
         opt.zero_grad(set_to_none=True)
-        loss.backward()
-        grad_bytes[0] = ldist.allreduce_gradients(enc)
+        loss.backward()  # includes the overlapped NCCL all-reduce of the encoder gradients
         opt.step()
         return loss
 
@@ -573,9 +572,9 @@ def run_train_arm(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"{args.config} training step: Swin-B + BERT forward (liblrce_b200 / HF), cross-modal "
-                                       f"encoder fwd+bwd (autograd), AdamW on the encoder, batch {B} clips/GPU, "
+                                       f"encoder fwd+bwd (hand-written kernels), AdamW on the encoder, batch {B} clips/GPU, "
                                        "temporal-scale 3, random-init weights", "global_batch": world * B,
-                           "parallelism": f"clip-sharded dp{world}" + (" + bucketed NCCL all-reduce" if world > 1 else ""),
+                           "parallelism": f"clip-sharded dp{world}" + (" + per-layer NCCL all-reduce overlapped with backward" if world > 1 else ""),
                            "grad_bytes_per_step": grad_bytes[0]},
                 "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
                         "d2h_bytes_per_step": 0},

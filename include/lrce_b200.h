@@ -152,7 +152,8 @@ int lrce_encoder_walk(const void* layer_table, int n_layers, const void* kv_vide
 
 /* ---- row / sequence kernels: BERT-base (text.py:5-17) and the encoder's training step (configs[4]) ----------------------
  * Dropout arguments: p (0 = off), a site id and a seed; the mask of element i is a counter-based hash of (seed, site, i), so
- * a backward call given the same triple regenerates the forward mask. "T" outputs are transposed bf16 copies
+ * a backward call given the same triple regenerates the forward mask. `seed_dev` (device pointer or NULL) is XOR-ed into the
+ * seed at run time, so launches captured in a CUDA graph draw a fresh mask on every replay. "T" outputs are transposed bf16 copies
  * T[col * ldT + rowT0 + row]: the K-major A / W operands of the weight-gradient GEMMs dW = dY^T X. */
 
 /* y = drop_out(LayerNorm(res + drop_a(a))) on 768-wide fp32 rows; res_bcast != 0: res is ONE row used for every row. Any of
@@ -160,27 +161,27 @@ int lrce_encoder_walk(const void* layer_table, int n_layers, const void* kv_vide
  * fusion_layer_norm (fusionv3.py:8-17, :47-49), BertSelfOutput / BertOutput LayerNorm. */
 int lrce_add_ln_768(const float* a, const float* res, int res_bcast, const float* gamma, const float* beta, float eps,
                     float* u_out, float* y_f32, void* y_bf16, void* yT, int ldT, int rowT0, long long n, float p_a, int site_a,
-                    float p_out, int site_out, unsigned long long seed, void* stream);
+                    float p_out, int site_out, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* backward of the step above: dy = (dy_a + dy_b) * mask_out; du fp32 (residual path), dub / dubT = du * mask_a in bf16 (branch
  * path); dgamma / dbeta fp32 [768] are ACCUMULATED (atomics). u = the forward's u_out. */
 int lrce_ln_bwd_768(const float* dy_a, const float* dy_b, const float* u, const float* gamma, float eps, float* du, void* dub,
                     void* dubT, int ldT, int rowT0, float* dgamma, float* dbeta, long long n, float p_a, int site_a, float p_out,
-                    int site_out, unsigned long long seed, void* stream);
+                    int site_out, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* fp32 [n, C] -> bf16 [n, C] (+ transposed copy): mode 0 cast, 1 GELU(erf) forward, 2 GELU backward (x = upstream gradient,
  * aux = forward pre-activation); dropout per element (group 1) or per `group` columns (64 = per attention head). */
 int lrce_rows_f32_to_bf16(const float* x, const float* aux, void* y, void* yT, int ldT, int rowT0, long long n, int C, int mode,
-                          int group, float p_drop, int site, unsigned long long seed, void* stream);
-int lrce_dropout_bf16(void* x, long long n_elems, float p_drop, int site, unsigned long long seed, void* stream);
+                          int group, float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
+int lrce_dropout_bf16(void* x, long long n_elems, float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* single-query cross attention of the summarisation token over [video segment `seg` ; text] (12 heads x 64; K at column
  * kcol + head*64 of the K/V GEMM output, V at + 768; q fp32 [R, 768] un-scaled). Forward keeps P fp32 [R*12, 256]. Backward
  * writes dq (bf16, x 1/8) and dK / dV into buffers laid out like kv_video / kv_text (video rows of a clip shared by
  * n_cand > 1 candidates are accumulated atomically: zero them first). nn.MultiheadAttention inside the decoder layer. */
 int lrce_xattn_fwd(const float* q, const void* kv_video, const void* kv_text, int ld_kv, int kcol, int R, int S, int seg, int Tv,
                    int Lt, int n_cand, float* P, void* ctx, void* ctxT, int ldT, int rowT0, float p_drop, int site,
-                   unsigned long long seed, void* stream);
+                   unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 int lrce_xattn_bwd(const float* q, const void* kv_video, const void* kv_text, int ld_kv, int kcol, int R, int S, int seg, int Tv,
                    int Lt, int n_cand, const float* P, const float* dctx, void* dq, void* dqT, int ldT, int rowT0, void* dkv_video,
-                   void* dkv_text, float p_drop, int site, unsigned long long seed, void* stream);
+                   void* dkv_text, float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* out[i] (+)= sum of the first `cols` entries of row i of src bf16 [rows, ld] (bias gradients from transposed operands) */
 int lrce_rowsum_bf16(const void* src, int ld, int cols, float* out, int rows, int accumulate, void* stream);
 /* out[c] += sum over rows of src[r, c] (fp32 or bf16 rows; out must be initialised) */
@@ -193,7 +194,7 @@ int lrce_add_bf16(void* dst, const void* a, const void* b, const void* c, long l
 int lrce_posembed_bwd(const float* dy, const void* proj, const void* text, int text_fp32, const float* emb_cls, const float* emb_pos,
                       const float* emb_len, const float* emb_clip, const float* gamma, float eps, void* dproj, float* d_cls,
                       float* d_pos, float* d_len, float* d_clip, float* dgamma, float* dbeta, int B, int S, int T, int P, int is_text,
-                      float p_drop, int site, unsigned long long seed, void* stream);
+                      float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* BertEmbeddings: LayerNorm(word[ids] + position[l] + token_type[type_ids]) -> fp32 + bf16 [n, 768]; n = n_seq * L */
 int lrce_bert_embed_ln(const long long* ids, const long long* type_ids, const float* word, const float* pos, const float* type,
                        const float* gamma, const float* beta, float eps, float* out_f32, void* out_bf16, long long n, int L,

@@ -45,7 +45,7 @@ def agent_args(tmp_path, dataset, **over):
     ns = argparse.Namespace(
         dataset=dataset, lr=[1e-5, 1e-5, 1e-5], min_lr=1e-7, use_cosine_scheduler=True, lr_restart_epoch=2,
         lr_restart_mul=1, lr_warm_up=0, lr_decay_factor=0.5, patience=2, reg_strength=1e-4, epoch=1, ckpt_interval=1,
-        log_dir=str(tmp_path), debug_mode=False, batch_size=2, num_workers=0, use_hinge_loss=True)
+        log_dir=str(tmp_path), debug_mode=False, batch_size=2, num_workers=0, use_hinge_loss=True, margin=1.0)
     for k, v in over.items():
         setattr(ns, k, v)
     return ns

@@ -112,10 +112,20 @@ def test_training_step_matches_inference_path_and_has_grads():
     g = torch.Generator().manual_seed(5)
     vf = torch.randn((2, 3, 3, 49, 1024), generator=g).bfloat16().cuda()
     tf = torch.randn((2, 30, 768), generator=g).cuda()
-    ya, yb = m2(vf, tf), m2(vf, tf)
-    assert not torch.equal(ya, yb) and torch.isfinite(ya).all() and torch.isfinite(yb).all()
-    ya.logsumexp(-1).sum().backward()
-    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m2.parameters())
+    ya = m2(vf, tf).detach()
+    for _ in range(3):  # direct launches, graph capture, graph replay: a fresh mask every time
+        yb = m2(vf, tf)
+        assert not torch.equal(ya, yb) and torch.isfinite(yb).all()
+        for q in m2.parameters():
+            q.grad = None
+        yb.logsumexp(-1).sum().backward()
+        assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in m2.parameters())
+        ya = yb.detach()
+    # two forwards before a backward: the plan holds ONE forward's activations -> loud error, not silent garbage
+    y1 = m2(vf, tf)
+    m2(vf, tf)
+    with pytest.raises(RuntimeError):
+        y1.sum().backward()
 
 
 def test_text_extractor_native_bert(golden, msvd, monkeypatch):

@@ -32,17 +32,17 @@ _SIGNATURES = {
     "lrce_debug_walk_timing": [_vp],
     "lrce_debug_attention_timing": [_vp],
     "lrce_encoder_walk": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "lrce_add_ln_768": [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _i, _f, _i, _u64, _vp],
-    "lrce_ln_bwd_768": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _ll, _f, _i, _f, _i, _u64, _vp],
-    "lrce_rows_f32_to_bf16": [_vp, _vp, _vp, _vp, _i, _i, _ll, _i, _i, _i, _f, _i, _u64, _vp],
-    "lrce_dropout_bf16": [_vp, _ll, _f, _i, _u64, _vp],
-    "lrce_xattn_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _u64, _vp],
-    "lrce_xattn_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _f, _i, _u64, _vp],
+    "lrce_add_ln_768": [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _i, _f, _i, _u64, _vp, _vp],
+    "lrce_ln_bwd_768": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _ll, _f, _i, _f, _i, _u64, _vp, _vp],
+    "lrce_rows_f32_to_bf16": [_vp, _vp, _vp, _vp, _i, _i, _ll, _i, _i, _i, _f, _i, _u64, _vp, _vp],
+    "lrce_dropout_bf16": [_vp, _ll, _f, _i, _u64, _vp, _vp],
+    "lrce_xattn_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _u64, _vp, _vp],
+    "lrce_xattn_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _f, _i, _u64, _vp, _vp],
     "lrce_rowsum_bf16": [_vp, _i, _i, _vp, _i, _i, _vp],
     "lrce_colsum": [_vp, _i, _ll, _i, _ll, _vp, _vp],
     "lrce_transpose_bf16": [_vp, _ll, _i, _ll, _vp, _ll, _vp],
     "lrce_add_bf16": [_vp, _vp, _vp, _vp, _ll, _vp],
-    "lrce_posembed_bwd": [_vp, _vp, _vp, _i] + [_vp] * 5 + [_f] + [_vp] * 7 + [_i] * 5 + [_f, _i, _u64, _vp],
+    "lrce_posembed_bwd": [_vp, _vp, _vp, _i] + [_vp] * 5 + [_f] + [_vp] * 7 + [_i] * 5 + [_f, _i, _u64, _vp, _vp],
     "lrce_bert_embed_ln": [_vp] * 7 + [_f, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "lrce_bert_attention": [_vp, _vp, _vp, _i, _i, _i, _vp],
 }

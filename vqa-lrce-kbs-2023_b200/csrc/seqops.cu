@@ -21,14 +21,17 @@ struct Drop {
   float p;      // 0 = off
   float scale;  // 1 / (1 - p)
   unsigned long long seed;
+  const unsigned long long* seed_dev;  // optional device-resident seed XOR-ed in at run time: a CUDA graph that captured
+                                       // this launch draws a fresh mask on every replay
   uint32_t site;
   uint32_t thresh;  // p * 2^32
 };
-__host__ inline Drop make_drop(float p, unsigned long long seed, int site) {
+__host__ inline Drop make_drop(float p, unsigned long long seed, const unsigned long long* seed_dev, int site) {
   Drop d;
   d.p = (p > 0.f && p < 1.f) ? p : 0.f;
   d.scale = d.p > 0.f ? 1.0f / (1.0f - d.p) : 1.0f;
   d.seed = seed;
+  d.seed_dev = seed_dev;
   d.site = static_cast<uint32_t>(site);
   d.thresh = static_cast<uint32_t>(static_cast<double>(d.p) * 4294967296.0);
   return d;
@@ -44,7 +47,8 @@ __device__ __forceinline__ uint32_t rng_u32(unsigned long long seed, uint32_t si
 // multiplier of element idx: 0 (dropped) or 1 / (1 - p)
 __device__ __forceinline__ float drop_mul(const Drop& d, uint32_t idx) {
   if (d.p <= 0.f) return 1.f;
-  return rng_u32(d.seed, d.site, idx) < d.thresh ? 0.f : d.scale;
+  const unsigned long long seed = d.seed_dev ? (d.seed ^ __ldg(d.seed_dev)) : d.seed;
+  return rng_u32(seed, d.site, idx) < d.thresh ? 0.f : d.scale;
 }
 
 __device__ __forceinline__ void row768_load_f32(float (&v)[24], const float* __restrict__ src, int lane) {
@@ -764,36 +768,36 @@ static inline unsigned blocks_for_rows(long long rows) { return static_cast<unsi
 
 extern "C" int lrce_add_ln_768(const float* a, const float* res, int res_bcast, const float* gamma, const float* beta, float eps,
                                float* u_out, float* y_f32, void* y_bf16, void* yT, int ldT, int rowT0, long long n, float p_a,
-                               int site_a, float p_out, int site_out, unsigned long long seed, void* stream) {
+                               int site_a, float p_out, int site_out, unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(res && gamma && beta && n > 0 && (y_f32 || y_bf16 || yT), "lrce_add_ln_768: bad arguments");
   AddLnParams p;
   p.a = a; p.res = res; p.res_bcast = res_bcast; p.gamma = gamma; p.beta = beta; p.eps = eps; p.u_out = u_out; p.y_f32 = y_f32;
   p.y_bf16 = reinterpret_cast<bf16*>(y_bf16); p.yT = reinterpret_cast<bf16*>(yT); p.ldT = ldT; p.rowT0 = rowT0; p.n = n;
-  p.drop_a = make_drop(p_a, seed, site_a);
-  p.drop_out = make_drop(p_out, seed, site_out);
+  p.drop_a = make_drop(p_a, seed, seed_dev, site_a);
+  p.drop_out = make_drop(p_out, seed, seed_dev, site_out);
   add_ln_kernel<<<blocks_for_rows(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("add_ln_kernel");
 }
 
 extern "C" int lrce_ln_bwd_768(const float* dy_a, const float* dy_b, const float* u, const float* gamma, float eps, float* du,
                                void* dub, void* dubT, int ldT, int rowT0, float* dgamma, float* dbeta, long long n, float p_a,
-                               int site_a, float p_out, int site_out, unsigned long long seed, void* stream) {
+                               int site_a, float p_out, int site_out, unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(dy_a && u && gamma && dgamma && dbeta && n > 0, "lrce_ln_bwd_768: bad arguments");
   LnBwdParams p;
   p.dy_a = dy_a; p.dy_b = dy_b; p.u = u; p.gamma = gamma; p.eps = eps; p.du = du; p.dub = reinterpret_cast<bf16*>(dub);
   p.dubT = reinterpret_cast<bf16*>(dubT); p.ldT = ldT; p.rowT0 = rowT0; p.dgamma = dgamma; p.dbeta = dbeta; p.n = n;
-  p.drop_a = make_drop(p_a, seed, site_a);
-  p.drop_out = make_drop(p_out, seed, site_out);
+  p.drop_a = make_drop(p_a, seed, seed_dev, site_a);
+  p.drop_out = make_drop(p_out, seed, seed_dev, site_out);
   ln_bwd_kernel<<<blocks_for_rows(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("ln_bwd_kernel");
 }
 
 extern "C" int lrce_rows_f32_to_bf16(const float* x, const float* aux, void* y, void* yT, int ldT, int rowT0, long long n, int C,
-                                     int mode, int group, float p_drop, int site, unsigned long long seed, void* stream) {
+                                     int mode, int group, float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(x && (y || yT) && n > 0 && C > 0 && C % 8 == 0 && mode >= 0 && mode <= 2 && group >= 1 && C % group == 0,
@@ -801,42 +805,42 @@ extern "C" int lrce_rows_f32_to_bf16(const float* x, const float* aux, void* y, 
   LRCE_REQUIRE(mode != ROWS_GELU_BWD || aux, "lrce_rows_f32_to_bf16: GELU backward needs the forward pre-activation");
   RowsParams p;
   p.x = x; p.aux = aux; p.y = reinterpret_cast<bf16*>(y); p.yT = reinterpret_cast<bf16*>(yT); p.ldT = ldT; p.rowT0 = rowT0;
-  p.n = n; p.C = C; p.mode = mode; p.group = group; p.drop = make_drop(p_drop, seed, site);
+  p.n = n; p.C = C; p.mode = mode; p.group = group; p.drop = make_drop(p_drop, seed, seed_dev, site);
   const long long threads = n * (C / 8);
   rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("rows_kernel");
 }
 
-extern "C" int lrce_dropout_bf16(void* x, long long n_elems, float p_drop, int site, unsigned long long seed, void* stream) {
+extern "C" int lrce_dropout_bf16(void* x, long long n_elems, float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(x && n_elems > 0 && n_elems % 8 == 0, "lrce_dropout_bf16: bad arguments");
   if (!(p_drop > 0.f)) return LRCE_OK;
   dropout_bf16_kernel<<<static_cast<unsigned>((n_elems / 8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<bf16*>(x), n_elems / 8, make_drop(p_drop, seed, site));
+      reinterpret_cast<bf16*>(x), n_elems / 8, make_drop(p_drop, seed, seed_dev, site));
   return check_launch("dropout_bf16_kernel");
 }
 
 static int fill_xattn(XAttnParams* p, const float* q, const void* kv_video, const void* kv_text, int ld_kv, int kcol, int R, int S,
                       int seg, int Tv, int Lt, int n_cand, float* P, int ldT, int rowT0, float p_drop, int site,
-                      unsigned long long seed) {
+                      unsigned long long seed, const unsigned long long* seed_dev) {
   LRCE_REQUIRE(q && kv_video && kv_text && P && R > 0 && S > 0 && seg >= 0 && seg < S && Tv > 0 && Lt > 0 && n_cand > 0 &&
                    R % n_cand == 0 && Tv + Lt <= XA_MAXK && ld_kv % 8 == 0 && kcol % 8 == 0,
                "cross attention: bad arguments (R=%d S=%d seg=%d Tv=%d Lt=%d cand=%d)", R, S, seg, Tv, Lt, n_cand);
   p->q = q; p->kv_video = reinterpret_cast<const bf16*>(kv_video); p->kv_text = reinterpret_cast<const bf16*>(kv_text);
   p->ld_kv = ld_kv; p->kcol = kcol; p->R = R; p->S = S; p->seg = seg; p->Tv = Tv; p->Lt = Lt; p->n_cand = n_cand; p->P = P;
-  p->ldT = ldT; p->rowT0 = rowT0; p->drop = make_drop(p_drop, seed, site);
+  p->ldT = ldT; p->rowT0 = rowT0; p->drop = make_drop(p_drop, seed, seed_dev, site);
   p->ctx = nullptr; p->ctxT = nullptr; p->dctx = nullptr; p->dq = nullptr; p->dqT = nullptr; p->dkv_video = nullptr; p->dkv_text = nullptr;
   return LRCE_OK;
 }
 
 extern "C" int lrce_xattn_fwd(const float* q, const void* kv_video, const void* kv_text, int ld_kv, int kcol, int R, int S, int seg,
                               int Tv, int Lt, int n_cand, float* P, void* ctx, void* ctxT, int ldT, int rowT0, float p_drop,
-                              int site, unsigned long long seed, void* stream) {
+                              int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   XAttnParams p;
-  rc = fill_xattn(&p, q, kv_video, kv_text, ld_kv, kcol, R, S, seg, Tv, Lt, n_cand, P, ldT, rowT0, p_drop, site, seed);
+  rc = fill_xattn(&p, q, kv_video, kv_text, ld_kv, kcol, R, S, seg, Tv, Lt, n_cand, P, ldT, rowT0, p_drop, site, seed, seed_dev);
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(ctx, "lrce_xattn_fwd: null output");
   p.ctx = reinterpret_cast<bf16*>(ctx); p.ctxT = reinterpret_cast<bf16*>(ctxT);
@@ -846,11 +850,11 @@ extern "C" int lrce_xattn_fwd(const float* q, const void* kv_video, const void* 
 
 extern "C" int lrce_xattn_bwd(const float* q, const void* kv_video, const void* kv_text, int ld_kv, int kcol, int R, int S, int seg,
                               int Tv, int Lt, int n_cand, const float* P, const float* dctx, void* dq, void* dqT, int ldT, int rowT0,
-                              void* dkv_video, void* dkv_text, float p_drop, int site, unsigned long long seed, void* stream) {
+                              void* dkv_video, void* dkv_text, float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   XAttnParams p;
-  rc = fill_xattn(&p, q, kv_video, kv_text, ld_kv, kcol, R, S, seg, Tv, Lt, n_cand, const_cast<float*>(P), ldT, rowT0, p_drop, site, seed);
+  rc = fill_xattn(&p, q, kv_video, kv_text, ld_kv, kcol, R, S, seg, Tv, Lt, n_cand, const_cast<float*>(P), ldT, rowT0, p_drop, site, seed, seed_dev);
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(dctx && dq && dkv_video && dkv_text, "lrce_xattn_bwd: null argument");
   p.dctx = dctx; p.dq = reinterpret_cast<bf16*>(dq); p.dqT = reinterpret_cast<bf16*>(dqT);
@@ -907,7 +911,7 @@ extern "C" int lrce_posembed_bwd(const float* dy, const void* proj, const void* 
                                  const float* emb_pos, const float* emb_len, const float* emb_clip, const float* gamma, float eps,
                                  void* dproj, float* d_cls, float* d_pos, float* d_len, float* d_clip, float* dgamma, float* dbeta,
                                  int B, int S, int T, int P, int is_text, float p_drop, int site, unsigned long long seed,
-                                 void* stream) {
+                                 const unsigned long long* seed_dev, void* stream) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(dy && emb_cls && emb_pos && gamma && d_cls && d_pos && dgamma && dbeta && B > 0 && S > 0 && T > 0 && P > 0,
@@ -921,7 +925,7 @@ extern "C" int lrce_posembed_bwd(const float* dy, const void* proj, const void* 
   p.emb_cls = emb_cls; p.emb_pos = emb_pos; p.emb_len = emb_len; p.emb_clip = emb_clip; p.gamma = gamma; p.eps = eps;
   p.dproj = reinterpret_cast<bf16*>(dproj); p.d_cls = d_cls; p.d_pos = d_pos; p.d_len = d_len; p.d_clip = d_clip;
   p.dgamma = dgamma; p.dbeta = dbeta; p.B = B; p.S = S; p.T = T; p.P = P; p.is_text = is_text;
-  p.drop = make_drop(p_drop, seed, site);
+  p.drop = make_drop(p_drop, seed, seed_dev, site);
   const long long rows = static_cast<long long>(B) * S * T * (P + 1);
   posembed_bwd_kernel<<<blocks_for_rows(rows), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("posembed_bwd_kernel");

@@ -47,7 +47,8 @@ class E2EBase(nn.Module):
         # stream; BERT's ~200 short library kernels then go to a side stream, so they run inside Swin's shadow instead
         # of in front of it, and their launch overhead is hidden too.
         cur = torch.cuda.current_stream()
-        side = self._side_stream(video_clips.device)
+        # (per-launch tracing, bench.py's kernel table: everything on one stream so that event intervals do not overlap)
+        side = cur if ops.trace is not None else self._side_stream(video_clips.device)
         side.wait_stream(cur)
         # The extractors are forward-only kernels: in a training step (grad enabled) they run without autograd and only
         # the cross-modal encoder is differentiated — the trainable part BASELINE.json's config 5 names.

@@ -382,6 +382,13 @@ class TextExtractor(_PackedModule):
         return pk
 
     def _native(self, input_ids, attention_mask, token_type_ids):
+        prev, ops.scope = ops.scope, "bert"
+        try:
+            return self._native_impl(input_ids, attention_mask, token_type_ids)
+        finally:
+            ops.scope = prev
+
+    def _native_impl(self, input_ids, attention_mask, token_type_ids):
         pk = self.packed()
         if input_ids.dim() != 2:
             raise ops._lib.LrceError(f"expected input_ids (B, L), got {tuple(input_ids.shape)}")

@@ -209,14 +209,18 @@ class LRCEOpenEnded(_PackedModule):
     def _wants_grad(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def _train_pack(self):
-        """bf16 operands of the training step (train.pack_train), rebuilt when a parameter changed"""
-        sig = self._packed.signature(self)
-        if getattr(self, "_tpack_sig", None) != sig:
-            from . import train
+    def _train_plan(self, B, S, T, P, Dv, R, L, n_cand, text_dtype, p, dev):
+        """fixed-address buffers + CUDA graphs of the training step for one problem shape (train._Plan)"""
+        from . import train
 
-            self._tpack, self._tpack_sig = train.pack_train(self), sig
-        return self._tpack
+        key = (B, S, T, P, Dv, R, L, n_cand, text_dtype, p, dev, tuple(q.data_ptr() for q in self.parameters()))
+        plans = self.__dict__.setdefault("_plans", {})
+        plan = plans.get(key)
+        if plan is None:
+            if len(plans) >= 2:  # a plan holds ~2 GB at batch 32: keep the two most recent shapes (train + validation batch)
+                plans.pop(next(iter(plans)))
+            plan = plans[key] = train._Plan(self, B, S, T, P, Dv, R, L, n_cand, text_dtype, p, dev)
+        return plan
 
     def _encode_train(self, video_features, text_features, n_cand, act=ops.ACT_NONE):
         """differentiable forward (grad enabled): the hand-written training kernels behind one autograd node (train.py);

@@ -11,6 +11,9 @@ BIAS_PITCH = 160
 
 # count of kernels launched through this module (bench.py reports it as gpu_launches)
 launches = 0
+# label appended to the entry-point names in `trace` ("bert", "train"): keeps BERT's / the training step's GEMMs out of the
+# Swin + encoder GEMM family that bench.py's roofline is computed on
+scope = ""
 
 
 def _ptr(t):
@@ -52,7 +55,7 @@ def _call(name, *args, work=None):
     _lib.check(getattr(_lib.lib(), name)(*args), name)
     e1.record()
     tag, flops, nbytes = work if work is not None else ("", 0, 0)
-    trace.append((name, tag, flops, nbytes, e0, e1))
+    trace.append((name + ("@" + scope if scope else ""), tag, flops, nbytes, e0, e1))
 
 
 def stats_chunk(width):
@@ -179,22 +182,28 @@ def window_attention(qkv, bias_dense, n_seg, D, H, W, C, n_heads, shift_hw, out=
     return out
 
 
-def video_posembed_ln(proj, emb_cls, emb_pos, emb_len, emb_clip, gamma, beta, eps, B, S, T, P):
+def video_posembed_ln(proj, emb_cls, emb_pos, emb_len, emb_clip, gamma, beta, eps, B, S, T, P, out=None):
     _req(proj, torch.bfloat16, "proj")
     assert proj.is_contiguous() and proj.shape == (B * S * T * P, 768)
-    out = torch.empty((B, S, T * (P + 1), 768), device=proj.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty((B, S, T * (P + 1), 768), device=proj.device, dtype=torch.bfloat16)
+    _req(out, torch.bfloat16, "out")
+    assert out.is_contiguous() and out.numel() == B * S * T * (P + 1) * 768
     _call("lrce_video_posembed_ln", _ptr(proj), _ptr(emb_cls), _ptr(emb_pos), _ptr(emb_len), _ptr(emb_clip), _ptr(gamma),
           _ptr(beta), float(eps), _ptr(out), B, S, T, P, _stream())
     return out
 
 
-def text_posembed_ln(text, emb_cls, emb_pos, gamma, beta, eps):
+def text_posembed_ln(text, emb_cls, emb_pos, gamma, beta, eps, out=None):
     if text.dtype not in (torch.bfloat16, torch.float32):
         raise _lib.LrceError(f"text features must be bf16 or fp32, got {text.dtype}")
     _req(text, text.dtype, "text")
     assert text.is_contiguous() and text.dim() == 3 and text.shape[2] == 768
     Bt, L, _ = text.shape
-    out = torch.empty((Bt, L + 1, 768), device=text.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty((Bt, L + 1, 768), device=text.device, dtype=torch.bfloat16)
+    _req(out, torch.bfloat16, "out")
+    assert out.is_contiguous() and out.numel() == Bt * (L + 1) * 768
     _call("lrce_text_posembed_ln", _ptr(text), int(text.dtype == torch.float32), _ptr(emb_cls), _ptr(emb_pos), _ptr(gamma), _ptr(beta), float(eps), _ptr(out),
           Bt, L, _stream())
     return out
@@ -232,6 +241,14 @@ ROWS_CAST, ROWS_GELU_FWD, ROWS_GELU_BWD = 0, 1, 2
 XATTN_MAXK = 256
 
 
+def _seed_args(seed):
+    """(host seed, device seed pointer): `seed` is an int, or a (int, int64 device tensor) pair whose tensor is XOR-ed in at run
+    time (fresh dropout masks for launches replayed from a CUDA graph)"""
+    if isinstance(seed, tuple):
+        return int(seed[0]), seed[1].data_ptr()
+    return int(seed), 0
+
+
 def _t(tT):
     """(pointer, ld, row offset) of an optional transposed-copy target given as (tensor [cols, ld], row offset)"""
     if tT is None:
@@ -250,7 +267,7 @@ def add_ln(a, res, gamma, beta, eps, *, res_bcast=False, u_out=None, y_f32=None,
     n = (a if a is not None else (y_f32 if y_f32 is not None else y_bf16)).numel() // 768
     tp, ld, r0 = _t(yT)
     _call("lrce_add_ln_768", _ptr(a), _ptr(res), int(res_bcast), _ptr(gamma), _ptr(beta), float(eps), _ptr(u_out), _ptr(y_f32),
-          _ptr(y_bf16), tp, ld, r0, n, float(p_a), int(site_a), float(p_out), int(site_out), int(seed), _stream())
+          _ptr(y_bf16), tp, ld, r0, n, float(p_a), int(site_a), float(p_out), int(site_out), *_seed_args(seed), _stream())
 
 
 def ln_bwd(dy_a, dy_b, u, gamma, eps, dgamma, dbeta, *, du=None, dub=None, dubT=None, p_a=0.0, site_a=0, p_out=0.0, site_out=0,
@@ -260,7 +277,7 @@ def ln_bwd(dy_a, dy_b, u, gamma, eps, dgamma, dbeta, *, du=None, dub=None, dubT=
     n = u.numel() // 768
     tp, ld, r0 = _t(dubT)
     _call("lrce_ln_bwd_768", _ptr(dy_a), _ptr(dy_b), _ptr(u), _ptr(gamma), float(eps), _ptr(du), _ptr(dub), tp, ld, r0,
-          _ptr(dgamma), _ptr(dbeta), n, float(p_a), int(site_a), float(p_out), int(site_out), int(seed), _stream())
+          _ptr(dgamma), _ptr(dbeta), n, float(p_a), int(site_a), float(p_out), int(site_out), *_seed_args(seed), _stream())
 
 
 def rows_to_bf16(x, *, aux=None, y=None, yT=None, mode=ROWS_CAST, group=1, p=0.0, site=0, seed=0):
@@ -278,7 +295,7 @@ def dropout_bf16_(x, p, site, seed):
     _req(x, torch.bfloat16, "x")
     assert x.is_contiguous()
     if p > 0:
-        _call("lrce_dropout_bf16", _ptr(x), x.numel(), float(p), int(site), int(seed), _stream())
+        _call("lrce_dropout_bf16", _ptr(x), x.numel(), float(p), int(site), *_seed_args(seed), _stream())
     return x
 
 
@@ -288,7 +305,7 @@ def xattn_fwd(q, kv_video, kv_text, kcol, R, S, seg, Tv, Lt, n_cand, P, ctx, ctx
     assert kv_video.stride(0) == kv_text.stride(0) and P.numel() >= R * 12 * XATTN_MAXK
     tp, ld, r0 = _t(ctxT)
     _call("lrce_xattn_fwd", _ptr(q), _ptr(kv_video), _ptr(kv_text), kv_video.stride(0), kcol, R, S, seg, Tv, Lt, n_cand, _ptr(P),
-          _ptr(ctx), tp, ld, r0, float(p), int(site), int(seed), _stream())
+          _ptr(ctx), tp, ld, r0, float(p), int(site), *_seed_args(seed), _stream())
 
 
 def xattn_bwd(q, kv_video, kv_text, kcol, R, S, seg, Tv, Lt, n_cand, P, dctx, dq, dkv_video, dkv_text, dqT=None, p=0.0, site=0,
@@ -298,7 +315,7 @@ def xattn_bwd(q, kv_video, kv_text, kcol, R, S, seg, Tv, Lt, n_cand, P, dctx, dq
     assert dkv_video.stride(0) == kv_video.stride(0) == dkv_text.stride(0) == kv_text.stride(0)
     tp, ld, r0 = _t(dqT)
     _call("lrce_xattn_bwd", _ptr(q), _ptr(kv_video), _ptr(kv_text), kv_video.stride(0), kcol, R, S, seg, Tv, Lt, n_cand, _ptr(P),
-          _ptr(dctx), _ptr(dq), tp, ld, r0, _ptr(dkv_video), _ptr(dkv_text), float(p), int(site), int(seed), _stream())
+          _ptr(dctx), _ptr(dq), tp, ld, r0, _ptr(dkv_video), _ptr(dkv_text), float(p), int(site), *_seed_args(seed), _stream())
 
 
 def rowsum_bf16(src, cols, out, accumulate=False):
@@ -337,7 +354,7 @@ def posembed_bwd(dy, *, proj=None, text=None, emb_cls, emb_pos, emb_len=None, em
     _call("lrce_posembed_bwd", _ptr(dy), _ptr(proj), _ptr(text), int(text is not None and text.dtype == torch.float32),
           _ptr(emb_cls), _ptr(emb_pos), _ptr(emb_len), _ptr(emb_clip), _ptr(gamma), float(eps), _ptr(dproj), _ptr(d_cls),
           _ptr(d_pos), _ptr(d_len), _ptr(d_clip), _ptr(dgamma), _ptr(dbeta), B, S, T, P, int(is_text), float(p), int(site),
-          int(seed), _stream())
+          *_seed_args(seed), _stream())
 
 
 def bert_embed_ln(ids, type_ids, word, pos, type_emb, gamma, beta, eps):

@@ -286,7 +286,7 @@ def rows_to_bf16(x, *, aux=None, y=None, yT=None, mode=ROWS_CAST, group=1, p=0.0
     assert x.is_contiguous() and x.dim() == 2
     n, C = x.shape
     tp, ld, r0 = _t(yT)
-    _call("lrce_rows_f32_to_bf16", _ptr(x), _ptr(aux), _ptr(y), tp, ld, r0, n, C, mode, group, float(p), int(site), int(seed),
+    _call("lrce_rows_f32_to_bf16", _ptr(x), _ptr(aux), _ptr(y), tp, ld, r0, n, C, mode, group, float(p), int(site), *_seed_args(seed),
           _stream())
     return y
 

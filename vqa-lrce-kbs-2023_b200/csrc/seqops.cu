@@ -166,47 +166,68 @@ struct LnBwdParams {
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (row >= p.n) return;
-  float u[24], dy[24];
-  row768_load_f32(u, p.u + row * ENC_D, lane);
-  row768_load_f32(dy, p.dy_a + row * ENC_D, lane);
-  if (p.dy_b) {
-    float b[24];
-    row768_load_f32(b, p.dy_b + row * ENC_D, lane);
+  __shared__ float red[8][ENC_D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  const bool active = row < p.n;
+  float u[24], dy[24], xg[24];  // xg: dy * xhat (gamma gradient of this row); dy keeps the beta gradient until the flush
 #pragma unroll
-    for (int i = 0; i < 24; ++i) dy[i] += b[i];
-  }
-  float mean, rstd;
-  row768_stats(u, p.eps, mean, rstd);
-  float sg = 0.f, sgx = 0.f;
+  for (int i = 0; i < 24; ++i) u[i] = dy[i] = xg[i] = 0.f;
+  if (active) {
+    row768_load_f32(u, p.u + row * ENC_D, lane);
+    row768_load_f32(dy, p.dy_a + row * ENC_D, lane);
+    if (p.dy_b) {
+      float b[24];
+      row768_load_f32(b, p.dy_b + row * ENC_D, lane);
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = (c * 32 + lane) * 8 + j, i = c * 8 + j;
-      dy[i] *= drop_mul(p.drop_out, static_cast<uint32_t>(row * ENC_D + col));
-      u[i] = (u[i] - mean) * rstd;  // xhat
-      atomicAdd(p.dgamma + col, dy[i] * u[i]);
-      atomicAdd(p.dbeta + col, dy[i]);
-      dy[i] *= __ldg(p.gamma + col);  // g
-      sg += dy[i];
-      sgx = fmaf(dy[i], u[i], sgx);
+      for (int i = 0; i < 24; ++i) dy[i] += b[i];
     }
-  sg = warp_sum(sg) * (1.0f / ENC_D);
-  sgx = warp_sum(sgx) * (1.0f / ENC_D);
-#pragma unroll
-  for (int i = 0; i < 24; ++i) dy[i] = rstd * (dy[i] - sg - u[i] * sgx);
-  if (p.du) row768_store_f32(dy, p.du + row * ENC_D, lane);
-  if (p.dub || p.dubT) {
+    float mean, rstd;
+    row768_stats(u, p.eps, mean, rstd);
+    float g[24], sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dy[c * 8 + j] *= drop_mul(p.drop_a, static_cast<uint32_t>(row * ENC_D + (c * 32 + lane) * 8 + j));
-    if (p.dub) row768_store_bf16(dy, p.dub + row * ENC_D, lane);
-    if (p.dubT) row768_store_T(dy, p.dubT, p.ldT, p.rowT0 + row, lane);
+      for (int j = 0; j < 8; ++j) {
+        const int col = (c * 32 + lane) * 8 + j, i = c * 8 + j;
+        dy[i] *= drop_mul(p.drop_out, static_cast<uint32_t>(row * ENC_D + col));
+        u[i] = (u[i] - mean) * rstd;  // xhat
+        xg[i] = dy[i] * u[i];
+        g[i] = dy[i] * __ldg(p.gamma + col);
+        sg += g[i];
+        sgx = fmaf(g[i], u[i], sgx);
+      }
+    sg = warp_sum(sg) * (1.0f / ENC_D);
+    sgx = warp_sum(sgx) * (1.0f / ENC_D);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) g[i] = rstd * (g[i] - sg - u[i] * sgx);
+    if (p.du) row768_store_f32(g, p.du + row * ENC_D, lane);
+    if (p.dub || p.dubT) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[c * 8 + j] *= drop_mul(p.drop_a, static_cast<uint32_t>(row * ENC_D + (c * 32 + lane) * 8 + j));
+      if (p.dub) row768_store_bf16(g, p.dub + row * ENC_D, lane);
+      if (p.dubT) row768_store_T(g, p.dubT, p.ldT, p.rowT0 + row, lane);
+    }
   }
+  // gamma / beta gradients: sum the CTA's 8 rows in shared memory, then one atomic per column and CTA
+  auto flush = [&](const float (&acc)[24], float* dst) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][(c * 32 + lane) * 8 + j] = acc[c * 8 + j];
+    __syncthreads();
+    for (int col = threadIdx.x; col < ENC_D; col += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][col];
+      atomicAdd(dst + col, v);
+    }
+  };
+  flush(xg, p.dgamma);
+  flush(dy, p.dbeta);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -317,199 +338,176 @@ __device__ __forceinline__ bf16* xa_dkey_row(const XAttnParams& p, int b, int j)
                   : p.dkv_text + (static_cast<size_t>(b) * p.Lt + (j - p.Tv)) * p.ld_kv;
 }
 
-__global__ void __launch_bounds__(128) xattn_fwd_kernel(const XAttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const int unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (unit >= p.R * 12) return;
-  const int b = unit / 12, head = unit % 12;
+// One CTA (128 threads) per (row, head). The head's K and V slices (n_keys x 64 bf16 each) are staged in shared memory with
+// coalesced 16-byte loads (row pitch 144 B: conflict-free when a thread reads one key's whole row); thread = key for the
+// score / dV / dK passes, thread = (head dim, key half) for the P V / dq passes.
+constexpr int XA_PITCH = 72;  // bf16 elements per staged key row
+constexpr int XA_THREADS = 128;
+constexpr int XA_SMEM = 2 * XA_MAXK * XA_PITCH * 2 + (XA_MAXK + 64 + 64 + 2 * 64 + 8) * 4;
+
+struct XaSmem {
+  bf16* K;
+  bf16* V;
+  float* s;     // [XA_MAXK] scores / probabilities / dS
+  float* q;     // [64]
+  float* dc;    // [64]
+  float* part;  // [2][64] partial sums of the two key halves
+  float* red;   // [8] cross-warp reduction scratch
+};
+__device__ __forceinline__ XaSmem xa_carve(uint8_t* smem) {
+  XaSmem m;
+  m.K = reinterpret_cast<bf16*>(smem);
+  m.V = m.K + XA_MAXK * XA_PITCH;
+  m.s = reinterpret_cast<float*>(m.V + XA_MAXK * XA_PITCH);
+  m.q = m.s + XA_MAXK;
+  m.dc = m.q + 64;
+  m.part = m.dc + 64;
+  m.red = m.part + 128;
+  return m;
+}
+__device__ __forceinline__ void xa_stage_kv(const XAttnParams& p, const XaSmem& m, int b, int head, int n_keys) {
+  for (int c = threadIdx.x; c < n_keys * 16; c += XA_THREADS) {
+    const int j = c >> 4, part = (c >> 3) & 1, ch = c & 7;  // part 0: K, 1: V
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xa_key_row(p, b, j) + p.kcol + part * ENC_D + head * 64) + ch);
+    *reinterpret_cast<uint4*>((part ? m.V : m.K) + j * XA_PITCH + ch * 8) = v;
+  }
+}
+__device__ __forceinline__ float xa_dot64(const bf16* row, const float* vec) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + 8 * i);
+    float2 f;
+    f = unpack_bf16x2(u.x); acc = fmaf(vec[8 * i + 0], f.x, acc); acc = fmaf(vec[8 * i + 1], f.y, acc);
+    f = unpack_bf16x2(u.y); acc = fmaf(vec[8 * i + 2], f.x, acc); acc = fmaf(vec[8 * i + 3], f.y, acc);
+    f = unpack_bf16x2(u.z); acc = fmaf(vec[8 * i + 4], f.x, acc); acc = fmaf(vec[8 * i + 5], f.y, acc);
+    f = unpack_bf16x2(u.w); acc = fmaf(vec[8 * i + 6], f.x, acc); acc = fmaf(vec[8 * i + 7], f.y, acc);
+  }
+  return acc;
+}
+// block-wide sum / max over the 4 warps (result in every thread)
+template <bool IS_MAX>
+__device__ __forceinline__ float xa_block_reduce(float v, float* red) {
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  __syncthreads();  // `red` may still be read from a previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < XA_THREADS / 32; ++w) r = IS_MAX ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+// out[d] = scale * sum_j w[j] M[j][d] for the 64 head dims: thread (d = tid & 63, half = tid >> 6) takes every other key
+__device__ __forceinline__ float xa_weighted_rows(const bf16* M, const float* w, int n_keys, float* part) {
+  const int d = threadIdx.x & 63, half = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (int j = half; j < n_keys; j += 2) acc = fmaf(w[j], __bfloat162float(M[j * XA_PITCH + d]), acc);
+  part[half * 64 + d] = acc;
+  __syncthreads();
+  return part[d] + part[64 + d];
+}
+
+__global__ void __launch_bounds__(XA_THREADS) xattn_fwd_kernel(const XAttnParams p) {
+  extern __shared__ __align__(16) uint8_t xa_smem[];
+  const XaSmem m = xa_carve(xa_smem);
+  const int unit = blockIdx.x, b = unit / 12, head = unit % 12, tid = threadIdx.x;
   const int n_keys = p.Tv + p.Lt;
-  float q[64];
-  {
-    const float4* qp = reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * ENC_D + head * 64);
+  xa_stage_kv(p, m, b, head, n_keys);
+  if (tid < 64) m.q[tid] = __ldg(p.q + static_cast<size_t>(b) * ENC_D + head * 64 + tid) * 0.125f;
+  __syncthreads();
+  float s[2], mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 a = __ldg(qp + i);
-      q[4 * i] = a.x * 0.125f; q[4 * i + 1] = a.y * 0.125f; q[4 * i + 2] = a.z * 0.125f; q[4 * i + 3] = a.w * 0.125f;
-    }
+  for (int t = 0; t < 2; ++t) {
+    const int j = t * XA_THREADS + tid;
+    s[t] = j < n_keys ? xa_dot64(m.K + j * XA_PITCH, m.q) : -INFINITY;
+    mx = fmaxf(mx, s[t]);
   }
-  float s[XA_MAXK / 32];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int t = 0; t < XA_MAXK / 32; ++t) {
-    const int j = t * 32 + lane;
-    s[t] = -INFINITY;
-    if (j < n_keys) {
-      const uint4* kp = reinterpret_cast<const uint4*>(xa_key_row(p, b, j) + p.kcol + head * 64);
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(kp + i);
-        float2 f;
-        f = unpack_bf16x2(u.x); acc = fmaf(q[8 * i + 0], f.x, acc); acc = fmaf(q[8 * i + 1], f.y, acc);
-        f = unpack_bf16x2(u.y); acc = fmaf(q[8 * i + 2], f.x, acc); acc = fmaf(q[8 * i + 3], f.y, acc);
-        f = unpack_bf16x2(u.z); acc = fmaf(q[8 * i + 4], f.x, acc); acc = fmaf(q[8 * i + 5], f.y, acc);
-        f = unpack_bf16x2(u.w); acc = fmaf(q[8 * i + 6], f.x, acc); acc = fmaf(q[8 * i + 7], f.y, acc);
-      }
-      s[t] = acc;
-      mx = fmaxf(mx, acc);
-    }
-  }
-  mx = warp_max(mx);
+  mx = xa_block_reduce<true>(mx, m.red);
   float sum = 0.f;
 #pragma unroll
-  for (int t = 0; t < XA_MAXK / 32; ++t) {
-    s[t] = (t * 32 + lane < n_keys) ? __expf(s[t] - mx) : 0.f;
+  for (int t = 0; t < 2; ++t) {
+    s[t] = (t * XA_THREADS + tid < n_keys) ? __expf(s[t] - mx) : 0.f;
     sum += s[t];
   }
-  sum = warp_sum(sum);
+  sum = xa_block_reduce<false>(sum, m.red);
   const float inv = 1.0f / sum;
   float* Prow = p.P + static_cast<size_t>(unit) * XA_MAXK;
 #pragma unroll
-  for (int t = 0; t < XA_MAXK / 32; ++t) {
-    s[t] *= inv;
-    Prow[t * 32 + lane] = s[t];
-    s[t] *= drop_mul(p.drop, static_cast<uint32_t>(unit * XA_MAXK + t * 32 + lane));
+  for (int t = 0; t < 2; ++t) {
+    const int j = t * XA_THREADS + tid;
+    const float pj = s[t] * inv;
+    Prow[j] = pj;
+    m.s[j] = pj * drop_mul(p.drop, static_cast<uint32_t>(unit * XA_MAXK + j));
   }
-  // ctx[d] = sum_j p'_j V_j[d]; lane owns dims 2 lane, 2 lane + 1
-  float o0 = 0.f, o1 = 0.f;
-  const int vcol = p.kcol + ENC_D + head * 64 + 2 * lane;
-#pragma unroll
-  for (int t = 0; t < XA_MAXK / 32; ++t) {
-    if (t * 32 >= n_keys) break;
-#pragma unroll 8
-    for (int l = 0; l < 32; ++l) {
-      const int j = t * 32 + l;
-      const float pj = __shfl_sync(0xffffffffu, s[t], l);
-      if (j < n_keys) {
-        const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(xa_key_row(p, b, j) + vcol)));
-        o0 = fmaf(pj, f.x, o0);
-        o1 = fmaf(pj, f.y, o1);
-      }
-    }
-  }
-  const int col = head * 64 + 2 * lane;
-  *reinterpret_cast<uint32_t*>(p.ctx + static_cast<size_t>(b) * ENC_D + col) = pack_bf16x2(o0, o1);
-  if (p.ctxT) {
-    p.ctxT[static_cast<size_t>(col) * p.ldT + p.rowT0 + b] = __float2bfloat16(o0);
-    p.ctxT[static_cast<size_t>(col + 1) * p.ldT + p.rowT0 + b] = __float2bfloat16(o1);
+  __syncthreads();
+  const float o = xa_weighted_rows(m.V, m.s, n_keys, m.part);
+  if (tid < 64) {
+    const int col = head * 64 + tid;
+    p.ctx[static_cast<size_t>(b) * ENC_D + col] = __float2bfloat16(o);
+    if (p.ctxT) p.ctxT[static_cast<size_t>(col) * p.ldT + p.rowT0 + b] = __float2bfloat16(o);
   }
 }
 
 template <bool ATOMIC_VIDEO>
-__global__ void __launch_bounds__(128) xattn_bwd_kernel(const XAttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const int unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (unit >= p.R * 12) return;
-  const int b = unit / 12, head = unit % 12;
+__global__ void __launch_bounds__(XA_THREADS) xattn_bwd_kernel(const XAttnParams p) {
+  extern __shared__ __align__(16) uint8_t xa_smem[];
+  const XaSmem m = xa_carve(xa_smem);
+  const int unit = blockIdx.x, b = unit / 12, head = unit % 12, tid = threadIdx.x;
   const int n_keys = p.Tv + p.Lt;
-  float dc[64];
-  {
-    const float4* dp = reinterpret_cast<const float4*>(p.dctx + static_cast<size_t>(b) * ENC_D + head * 64);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 a = __ldg(dp + i);
-      dc[4 * i] = a.x; dc[4 * i + 1] = a.y; dc[4 * i + 2] = a.z; dc[4 * i + 3] = a.w;
-    }
+  xa_stage_kv(p, m, b, head, n_keys);
+  if (tid < 64) {
+    m.q[tid] = __ldg(p.q + static_cast<size_t>(b) * ENC_D + head * 64 + tid) * 0.125f;
+    m.dc[tid] = __ldg(p.dctx + static_cast<size_t>(b) * ENC_D + head * 64 + tid);
   }
+  __syncthreads();
   const float* Prow = p.P + static_cast<size_t>(unit) * XA_MAXK;
-  float pj[XA_MAXK / 32], ds[XA_MAXK / 32];
-  float dsum = 0.f;
-  // pass 1 (lane = key): dP'_j = dctx . V_j ; dV_j = p'_j dctx ; D = sum_j P_j dP_j
+  // stores of one key's 64 gradient values (128 B): plain for rows this (row, head) owns, atomic for the video rows that
+  // the candidates of a multiple-choice clip share
+  auto store_row = [&](bf16* dst, float w, const float* vec, bool shared_row) {
 #pragma unroll
-  for (int t = 0; t < XA_MAXK / 32; ++t) {
-    const int j = t * 32 + lane;
-    pj[t] = 0.f;
-    ds[t] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      if (ATOMIC_VIDEO && shared_row) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          atomicAdd(reinterpret_cast<__nv_bfloat162*>(dst + 8 * i + 2 * k), __floats2bfloat162_rn(w * vec[8 * i + 2 * k], w * vec[8 * i + 2 * k + 1]));
+      } else {
+        uint4 o;
+        o.x = pack_bf16x2(w * vec[8 * i + 0], w * vec[8 * i + 1]); o.y = pack_bf16x2(w * vec[8 * i + 2], w * vec[8 * i + 3]);
+        o.z = pack_bf16x2(w * vec[8 * i + 4], w * vec[8 * i + 5]); o.w = pack_bf16x2(w * vec[8 * i + 6], w * vec[8 * i + 7]);
+        *reinterpret_cast<uint4*>(dst + 8 * i) = o;
+      }
+    }
+  };
+  // pass 1 (thread = key): dP'_j = dctx . V_j ; dV_j = p'_j dctx ; D = sum_j P_j dP_j
+  float pj[2], dp[2], dsum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int j = t * XA_THREADS + tid;
+    pj[t] = dp[t] = 0.f;
     if (j < n_keys) {
       pj[t] = Prow[j];
-      const float m = drop_mul(p.drop, static_cast<uint32_t>(unit * XA_MAXK + j));
-      const float pd = pj[t] * m;  // dropped probability used by the forward P V
-      const uint4* vp = reinterpret_cast<const uint4*>(xa_key_row(p, b, j) + p.kcol + ENC_D + head * 64);
-      bf16* dvp = xa_dkey_row(p, b, j) + p.kcol + ENC_D + head * 64;
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(vp + i);
-        float2 f;
-        f = unpack_bf16x2(u.x); acc = fmaf(dc[8 * i + 0], f.x, acc); acc = fmaf(dc[8 * i + 1], f.y, acc);
-        f = unpack_bf16x2(u.y); acc = fmaf(dc[8 * i + 2], f.x, acc); acc = fmaf(dc[8 * i + 3], f.y, acc);
-        f = unpack_bf16x2(u.z); acc = fmaf(dc[8 * i + 4], f.x, acc); acc = fmaf(dc[8 * i + 5], f.y, acc);
-        f = unpack_bf16x2(u.w); acc = fmaf(dc[8 * i + 6], f.x, acc); acc = fmaf(dc[8 * i + 7], f.y, acc);
-        if (ATOMIC_VIDEO && j < p.Tv) {  // multiple choice: the candidates of a clip share its video keys
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            atomicAdd(reinterpret_cast<__nv_bfloat162*>(dvp + 8 * i + 2 * k),
-                      __floats2bfloat162_rn(pd * dc[8 * i + 2 * k], pd * dc[8 * i + 2 * k + 1]));
-        } else {
-          uint4 o;
-          o.x = pack_bf16x2(pd * dc[8 * i + 0], pd * dc[8 * i + 1]); o.y = pack_bf16x2(pd * dc[8 * i + 2], pd * dc[8 * i + 3]);
-          o.z = pack_bf16x2(pd * dc[8 * i + 4], pd * dc[8 * i + 5]); o.w = pack_bf16x2(pd * dc[8 * i + 6], pd * dc[8 * i + 7]);
-          *reinterpret_cast<uint4*>(dvp + 8 * i) = o;
-        }
-      }
-      ds[t] = acc * m;  // dP_j
-      dsum = fmaf(pj[t], ds[t], dsum);
+      const float mk = drop_mul(p.drop, static_cast<uint32_t>(unit * XA_MAXK + j));
+      store_row(xa_dkey_row(p, b, j) + p.kcol + ENC_D + head * 64, pj[t] * mk, m.dc, j < p.Tv);
+      dp[t] = xa_dot64(m.V + j * XA_PITCH, m.dc) * mk;
+      dsum = fmaf(pj[t], dp[t], dsum);
     }
   }
-  dsum = warp_sum(dsum);
+  dsum = xa_block_reduce<false>(dsum, m.red);
+  // pass 2 (thread = key): dS_j = P_j (dP_j - D) ; dK_j = dS_j q / 8
 #pragma unroll
-  for (int t = 0; t < XA_MAXK / 32; ++t) ds[t] = pj[t] * (ds[t] - dsum);  // dS_j (w.r.t. the scaled score)
-  // pass 2 (lane = key): dK_j = dS_j q / 8
-  {
-    float qv[64];
-    const float4* qp = reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * ENC_D + head * 64);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 a = __ldg(qp + i);
-      qv[4 * i] = a.x * 0.125f; qv[4 * i + 1] = a.y * 0.125f; qv[4 * i + 2] = a.z * 0.125f; qv[4 * i + 3] = a.w * 0.125f;
-    }
-#pragma unroll
-    for (int t = 0; t < XA_MAXK / 32; ++t) {
-      const int j = t * 32 + lane;
-      if (j < n_keys) {
-        bf16* dkp = xa_dkey_row(p, b, j) + p.kcol + head * 64;
-        const float d = ds[t];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (ATOMIC_VIDEO && j < p.Tv) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              atomicAdd(reinterpret_cast<__nv_bfloat162*>(dkp + 8 * i + 2 * k),
-                        __floats2bfloat162_rn(d * qv[8 * i + 2 * k], d * qv[8 * i + 2 * k + 1]));
-          } else {
-            uint4 o;
-            o.x = pack_bf16x2(d * qv[8 * i + 0], d * qv[8 * i + 1]); o.y = pack_bf16x2(d * qv[8 * i + 2], d * qv[8 * i + 3]);
-            o.z = pack_bf16x2(d * qv[8 * i + 4], d * qv[8 * i + 5]); o.w = pack_bf16x2(d * qv[8 * i + 6], d * qv[8 * i + 7]);
-            *reinterpret_cast<uint4*>(dkp + 8 * i) = o;
-          }
-        }
-      }
-    }
+  for (int t = 0; t < 2; ++t) {
+    const int j = t * XA_THREADS + tid;
+    const float ds = pj[t] * (dp[t] - dsum);
+    m.s[j] = ds;
+    if (j < n_keys) store_row(xa_dkey_row(p, b, j) + p.kcol + head * 64, ds, m.q, j < p.Tv);
   }
-  // pass 3 (lane = two head dims): dq = sum_j dS_j K_j / 8
-  float g0 = 0.f, g1 = 0.f;
-  const int kc = p.kcol + head * 64 + 2 * lane;
-#pragma unroll
-  for (int t = 0; t < XA_MAXK / 32; ++t) {
-    if (t * 32 >= n_keys) break;
-#pragma unroll 8
-    for (int l = 0; l < 32; ++l) {
-      const int j = t * 32 + l;
-      const float d = __shfl_sync(0xffffffffu, ds[t], l);
-      if (j < n_keys) {
-        const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(xa_key_row(p, b, j) + kc)));
-        g0 = fmaf(d, f.x, g0);
-        g1 = fmaf(d, f.y, g1);
-      }
-    }
-  }
-  g0 *= 0.125f;
-  g1 *= 0.125f;
-  const int col = head * 64 + 2 * lane;
-  *reinterpret_cast<uint32_t*>(p.dq + static_cast<size_t>(b) * ENC_D + col) = pack_bf16x2(g0, g1);
-  if (p.dqT) {
-    p.dqT[static_cast<size_t>(col) * p.ldT + p.rowT0 + b] = __float2bfloat16(g0);
-    p.dqT[static_cast<size_t>(col + 1) * p.ldT + p.rowT0 + b] = __float2bfloat16(g1);
+  __syncthreads();
+  // pass 3: dq = sum_j dS_j K_j / 8
+  const float g = xa_weighted_rows(m.K, m.s, n_keys, m.part) * 0.125f;
+  if (tid < 64) {
+    const int col = head * 64 + tid;
+    p.dq[static_cast<size_t>(b) * ENC_D + col] = __float2bfloat16(g);
+    if (p.dqT) p.dqT[static_cast<size_t>(col) * p.ldT + p.rowT0 + b] = __float2bfloat16(g);
   }
 }
 
@@ -602,62 +600,84 @@ struct PosBwdParams {
   int is_text;
   Drop drop;  // dropout that was applied to the embedded rows
 };
+// One CTA (8 warps) per frame = the P + 1 rows that share (t, s): LayerNorm-parameter and emb_len / emb_clip gradients are
+// summed in registers over the frame's rows and across the warps in shared memory before ONE atomic per column and CTA
+// (14 400 video rows would otherwise queue 14 400 atomics on each of the 768 gamma addresses); emb_pos is per row.
 __global__ void __launch_bounds__(256) posembed_bwd_kernel(const PosBwdParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long rows = static_cast<long long>(p.B) * p.S * p.T * (p.P + 1);
-  if (row >= rows) return;
-  const int pp = static_cast<int>(row % (p.P + 1));
-  const long long frame = row / (p.P + 1);
+  __shared__ float red[8][ENC_D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long frame = blockIdx.x;  // (b * S + s) * T + t
   const int t = static_cast<int>(frame % p.T);
   const int s = static_cast<int>((frame / p.T) % p.S);
-  float v[24];
+  float acc_g[24], acc_b[24], acc_u[24];
 #pragma unroll
-  for (int i = 0; i < 24; ++i) v[i] = 0.f;
-  if (pp == 0) row768_add_f32(v, p.emb_cls, lane);
-  else if (!p.is_text) row768_add_bf16(v, p.proj + (frame * p.P + (pp - 1)) * ENC_D, lane);
-  else if (p.text_f32) row768_add_f32(v, p.text_f32 + (frame * p.P + (pp - 1)) * ENC_D, lane);
-  else row768_add_bf16(v, p.text_bf16 + (frame * p.P + (pp - 1)) * ENC_D, lane);
-  row768_add_f32(v, p.emb_pos + static_cast<size_t>(pp) * ENC_D, lane);
-  if (!p.is_text) {
-    row768_add_f32(v, p.emb_len + static_cast<size_t>(t) * ENC_D, lane);
-    row768_add_f32(v, p.emb_clip + static_cast<size_t>(s) * ENC_D, lane);
-  }
-  float mean, rstd;
-  row768_stats(v, p.eps, mean, rstd);
-  float dy[24];
-  row768_load_f32(dy, p.dy + row * ENC_D, lane);
-  float sg = 0.f, sgx = 0.f;
+  for (int i = 0; i < 24; ++i) acc_g[i] = acc_b[i] = acc_u[i] = 0.f;
+  for (int pp = warp; pp <= p.P; pp += 8) {
+    const long long row = frame * (p.P + 1) + pp;
+    float v[24];
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = (c * 32 + lane) * 8 + j, i = c * 8 + j;
-      dy[i] *= drop_mul(p.drop, static_cast<uint32_t>(row * ENC_D + col));
-      v[i] = (v[i] - mean) * rstd;
-      atomicAdd(p.dgamma + col, dy[i] * v[i]);
-      atomicAdd(p.dbeta + col, dy[i]);
-      dy[i] *= __ldg(p.gamma + col);
-      sg += dy[i];
-      sgx = fmaf(dy[i], v[i], sgx);
+    for (int i = 0; i < 24; ++i) v[i] = 0.f;
+    if (pp == 0) row768_add_f32(v, p.emb_cls, lane);
+    else if (!p.is_text) row768_add_bf16(v, p.proj + (frame * p.P + (pp - 1)) * ENC_D, lane);
+    else if (p.text_f32) row768_add_f32(v, p.text_f32 + (frame * p.P + (pp - 1)) * ENC_D, lane);
+    else row768_add_bf16(v, p.text_bf16 + (frame * p.P + (pp - 1)) * ENC_D, lane);
+    row768_add_f32(v, p.emb_pos + static_cast<size_t>(pp) * ENC_D, lane);
+    if (!p.is_text) {
+      row768_add_f32(v, p.emb_len + static_cast<size_t>(t) * ENC_D, lane);
+      row768_add_f32(v, p.emb_clip + static_cast<size_t>(s) * ENC_D, lane);
     }
-  sg = warp_sum(sg) * (1.0f / ENC_D);
-  sgx = warp_sum(sgx) * (1.0f / ENC_D);
+    float mean, rstd;
+    row768_stats(v, p.eps, mean, rstd);
+    float dy[24];
+    row768_load_f32(dy, p.dy + row * ENC_D, lane);
+    float sg = 0.f, sgx = 0.f;
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = (c * 32 + lane) * 8 + j, i = c * 8 + j;
-      const float du = rstd * (dy[i] - sg - v[i] * sgx);
-      dy[i] = du;
-      atomicAdd(p.d_pos + static_cast<size_t>(pp) * ENC_D + col, du);
-      if (pp == 0) atomicAdd(p.d_cls + col, du);
-      if (!p.is_text) {
-        atomicAdd(p.d_len + static_cast<size_t>(t) * ENC_D + col, du);
-        atomicAdd(p.d_clip + static_cast<size_t>(s) * ENC_D + col, du);
+      for (int j = 0; j < 8; ++j) {
+        const int col = (c * 32 + lane) * 8 + j, i = c * 8 + j;
+        dy[i] *= drop_mul(p.drop, static_cast<uint32_t>(row * ENC_D + col));
+        v[i] = (v[i] - mean) * rstd;
+        acc_g[i] = fmaf(dy[i], v[i], acc_g[i]);
+        acc_b[i] += dy[i];
+        dy[i] *= __ldg(p.gamma + col);
+        sg += dy[i];
+        sgx = fmaf(dy[i], v[i], sgx);
       }
+    sg = warp_sum(sg) * (1.0f / ENC_D);
+    sgx = warp_sum(sgx) * (1.0f / ENC_D);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = (c * 32 + lane) * 8 + j, i = c * 8 + j;
+        const float du = rstd * (dy[i] - sg - v[i] * sgx);
+        dy[i] = du;
+        acc_u[i] += du;
+        atomicAdd(p.d_pos + static_cast<size_t>(pp) * ENC_D + col, du);
+        if (pp == 0) atomicAdd(p.d_cls + col, du);
+      }
+    if (!p.is_text && pp > 0) row768_store_bf16(dy, p.dproj + (frame * p.P + (pp - 1)) * ENC_D, lane);
+  }
+  // cross-warp sums, one quantity at a time through the same shared buffer
+  auto flush = [&](const float (&acc)[24], float* dst0, float* dst1) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][(c * 32 + lane) * 8 + j] = acc[c * 8 + j];
+    __syncthreads();
+    for (int col = threadIdx.x; col < ENC_D; col += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][col];
+      atomicAdd(dst0 + col, v);
+      if (dst1) atomicAdd(dst1 + col, v);
     }
-  if (!p.is_text && pp > 0) row768_store_bf16(dy, p.dproj + (frame * p.P + (pp - 1)) * ENC_D, lane);
+  };
+  flush(acc_g, p.dgamma, nullptr);
+  flush(acc_b, p.dbeta, nullptr);
+  if (!p.is_text) flush(acc_u, p.d_len + static_cast<size_t>(t) * ENC_D, p.d_clip + static_cast<size_t>(s) * ENC_D);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -821,6 +841,21 @@ extern "C" int lrce_dropout_bf16(void* x, long long n_elems, float p_drop, int s
   return check_launch("dropout_bf16_kernel");
 }
 
+static int xa_configure() {
+  static thread_local uint64_t configured = 0;  // one bit per device
+  if (needs_device_setup(&configured)) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(xattn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(xattn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(xattn kernels, smem=%d): %s", XA_SMEM, cudaGetErrorString(e));
+      return LRCE_ECUDA;
+    }
+    mark_device_setup(&configured);
+  }
+  return LRCE_OK;
+}
+
 static int fill_xattn(XAttnParams* p, const float* q, const void* kv_video, const void* kv_text, int ld_kv, int kcol, int R, int S,
                       int seg, int Tv, int Lt, int n_cand, float* P, int ldT, int rowT0, float p_drop, int site,
                       unsigned long long seed, const unsigned long long* seed_dev) {
@@ -844,7 +879,9 @@ extern "C" int lrce_xattn_fwd(const float* q, const void* kv_video, const void* 
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(ctx, "lrce_xattn_fwd: null output");
   p.ctx = reinterpret_cast<bf16*>(ctx); p.ctxT = reinterpret_cast<bf16*>(ctxT);
-  xattn_fwd_kernel<<<(R * 12 + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  rc = xa_configure();
+  if (rc != LRCE_OK) return rc;
+  xattn_fwd_kernel<<<R * 12, XA_THREADS, XA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("xattn_fwd_kernel");
 }
 
@@ -860,8 +897,10 @@ extern "C" int lrce_xattn_bwd(const float* q, const void* kv_video, const void* 
   p.dctx = dctx; p.dq = reinterpret_cast<bf16*>(dq); p.dqT = reinterpret_cast<bf16*>(dqT);
   p.dkv_video = reinterpret_cast<bf16*>(dkv_video); p.dkv_text = reinterpret_cast<bf16*>(dkv_text);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (n_cand > 1) xattn_bwd_kernel<true><<<(R * 12 + 3) / 4, 128, 0, s>>>(p);
-  else xattn_bwd_kernel<false><<<(R * 12 + 3) / 4, 128, 0, s>>>(p);
+  rc = xa_configure();
+  if (rc != LRCE_OK) return rc;
+  if (n_cand > 1) xattn_bwd_kernel<true><<<R * 12, XA_THREADS, XA_SMEM, s>>>(p);
+  else xattn_bwd_kernel<false><<<R * 12, XA_THREADS, XA_SMEM, s>>>(p);
   return check_launch("xattn_bwd_kernel");
 }
 
@@ -926,8 +965,8 @@ extern "C" int lrce_posembed_bwd(const float* dy, const void* proj, const void* 
   p.dproj = reinterpret_cast<bf16*>(dproj); p.d_cls = d_cls; p.d_pos = d_pos; p.d_len = d_len; p.d_clip = d_clip;
   p.dgamma = dgamma; p.dbeta = dbeta; p.B = B; p.S = S; p.T = T; p.P = P; p.is_text = is_text;
   p.drop = make_drop(p_drop, seed, seed_dev, site);
-  const long long rows = static_cast<long long>(B) * S * T * (P + 1);
-  posembed_bwd_kernel<<<blocks_for_rows(rows), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  const long long frames = static_cast<long long>(B) * S * T;
+  posembed_bwd_kernel<<<static_cast<unsigned>(frames), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("posembed_bwd_kernel");
 }
 

@@ -195,6 +195,10 @@ int lrce_posembed_bwd(const float* dy, const void* proj, const void* text, int t
                       const float* emb_len, const float* emb_clip, const float* gamma, float eps, void* dproj, float* d_cls,
                       float* d_pos, float* d_len, float* d_clip, float* dgamma, float* dbeta, int B, int S, int T, int P, int is_text,
                       float p_drop, int site, unsigned long long seed, const unsigned long long* seed_dev, void* stream);
+/* out fp32 [M, N] = A bf16 [M, K] x W bf16 [N, K]^T (+ bias): the token-path products of the training step (M = a few dozen
+ * rows, K = 768 or 3072), bound by streaming W once; a 128-row tensor-core tile would be mostly padding. */
+int lrce_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, float* out, int ldo,
+                          void* stream);
 /* BertEmbeddings: LayerNorm(word[ids] + position[l] + token_type[type_ids]) -> fp32 + bf16 [n, 768]; n = n_seq * L */
 int lrce_bert_embed_ln(const long long* ids, const long long* type_ids, const float* word, const float* pos, const float* type,
                        const float* gamma, const float* beta, float eps, float* out_f32, void* out_bf16, long long n, int L,

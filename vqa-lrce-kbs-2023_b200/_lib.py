@@ -43,6 +43,7 @@ _SIGNATURES = {
     "lrce_transpose_bf16": [_vp, _ll, _i, _ll, _vp, _ll, _vp],
     "lrce_add_bf16": [_vp, _vp, _vp, _vp, _ll, _vp],
     "lrce_posembed_bwd": [_vp, _vp, _vp, _i] + [_vp] * 5 + [_f] + [_vp] * 7 + [_i] * 5 + [_f, _i, _u64, _vp, _vp],
+    "lrce_gemm_skinny_bf16": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "lrce_bert_embed_ln": [_vp] * 7 + [_f, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "lrce_bert_attention": [_vp, _vp, _vp, _i, _i, _i, _vp],
 }

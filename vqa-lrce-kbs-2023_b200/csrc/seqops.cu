@@ -681,6 +681,74 @@ __global__ void __launch_bounds__(256) posembed_bwd_kernel(const PosBwdParams p)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Skinny GEMM for the token path of the training step: out[M, N] fp32 = A[M, K] bf16 x W[N, K]^T (+ bias), M = a few dozen
+// rows (the summarisation tokens of a batch), K in {768, 3072}. A 128-row tcgen05 tile would be three-quarters padding and
+// the persistent GEMM's prologue (TMEM allocation, barrier ring, descriptor fetch) costs more than this whole product, which
+// is bound by streaming W once: a CTA owns 8 output columns of a 32-row tile, its 8 warps split K and stream their slices of
+// the 8 weight rows straight into mma.sync m16n8k16 B fragments (16-byte loads), the 32 activation rows sit in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SK_ROWS = 32, SK_WARPS = 8, SK_THREADS = 256;
+template <int NCH>  // 32-wide k chunks per warp: K = 8 * 32 * NCH
+__global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw,
+                                                                 const float* __restrict__ bias, float* __restrict__ out, int ldo, int M,
+                                                                 int N) {
+  constexpr int K = SK_WARPS * 32 * NCH;
+  constexpr int PITCH = K + 32;  // bf16 elements; (PITCH / 2) % 32 == 16 words: conflict-free 16-byte fragment loads
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  bf16* sX = reinterpret_cast<bf16*>(sk_smem);
+  float* sRed = reinterpret_cast<float*>(sk_smem + SK_ROWS * PITCH * 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int n0 = blockIdx.x * 8, r_base = blockIdx.y * SK_ROWS;
+  const int k_begin = warp * (NCH * 32);
+  // this warp's K slice of the tile's 8 weight rows: issued first, they do not depend on the activations
+  uint4 wreg[NCH];
+  {
+    const int nrow = min(n0 + g, N - 1);
+    const bf16* wrow = W + static_cast<size_t>(nrow) * ldw + k_begin + 8 * t4;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) wreg[c] = __ldg(reinterpret_cast<const uint4*>(wrow + c * 32));
+  }
+  for (int c = tid; c < SK_ROWS * (K / 8); c += SK_THREADS) {
+    const int r = c / (K / 8), k = (c - r * (K / 8)) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r_base + r < M) v = *reinterpret_cast<const uint4*>(A + static_cast<size_t>(r_base + r) * lda + k);
+    *reinterpret_cast<uint4*>(sX + static_cast<size_t>(r) * PITCH + k) = v;
+  }
+  __syncthreads();
+  const bf16* xa0 = sX + static_cast<size_t>(g) * PITCH + k_begin + 8 * t4;
+  float acc[2][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) acc[mi][0] = acc[mi][1] = acc[mi][2] = acc[mi][3] = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const uint4 xlo = *reinterpret_cast<const uint4*>(xa0 + static_cast<size_t>(mi * 16) * PITCH + c * 32);
+      const uint4 xhi = *reinterpret_cast<const uint4*>(xa0 + static_cast<size_t>(mi * 16 + 8) * PITCH + c * 32);
+      mma16816(acc[mi], xlo.x, xhi.x, xlo.y, xhi.y, wreg[c].x, wreg[c].y);
+      mma16816(acc[mi], xlo.z, xhi.z, xlo.w, xhi.w, wreg[c].z, wreg[c].w);
+    }
+  }
+  // cross-warp K reduction, bias, store
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    float* r = sRed + (warp * SK_ROWS + mi * 16 + g) * 8 + 2 * t4;
+    r[0] = acc[mi][0]; r[1] = acc[mi][1];
+    r[8 * 8] = acc[mi][2]; r[8 * 8 + 1] = acc[mi][3];
+  }
+  __syncthreads();
+  {
+    const int r = tid >> 3, col = tid & 7;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) v += sRed[(w * SK_ROWS + r) * 8 + col];
+    const int row = r_base + r, n = n0 + col;
+    if (row < M && n < N) out[static_cast<size_t>(row) * ldo + n] = v + (bias ? __ldg(bias + n) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // BERT (HF BertModel as text.py:9-17 uses it): embeddings + LayerNorm, and the masked multi-head self-attention
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bert_embed_ln_kernel(const long long* __restrict__ ids, const long long* __restrict__ type_ids,
@@ -991,4 +1059,35 @@ extern "C" int lrce_bert_attention(const void* qkv, const long long* mask, void*
   bert_attention_kernel<<<n_seq * n_heads, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(qkv), mask, reinterpret_cast<bf16*>(out), L, n_heads);
   return check_launch("bert_attention_kernel");
+}
+
+extern "C" int lrce_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, float* out,
+                                     int ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(A && W && out && M > 0 && N > 0, "lrce_gemm_skinny_bf16: bad arguments");
+  LRCE_REQUIRE(K == 768 || K == 3072, "lrce_gemm_skinny_bf16: K must be 768 or 3072 (got %d)", K);
+  LRCE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K && ldo >= N && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+               "lrce_gemm_skinny_bf16: operands must be 16-byte aligned with pitches that are multiples of 8 elements");
+  const int smem = SK_ROWS * (K + 32) * 2 + SK_WARPS * SK_ROWS * 8 * 4;
+  static thread_local uint64_t configured = 0;  // one bit per device
+  if (needs_device_setup(&configured)) {
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SK_ROWS * (768 + 32) * 2 + SK_WARPS * SK_ROWS * 8 * 4);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(skinny_gemm_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               SK_ROWS * (3072 + 32) * 2 + SK_WARPS * SK_ROWS * 8 * 4);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(skinny_gemm_kernel): %s", cudaGetErrorString(e));
+      return LRCE_ECUDA;
+    }
+    mark_device_setup(&configured);
+  }
+  dim3 grid((N + 7) / 8, (M + SK_ROWS - 1) / SK_ROWS);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bf16 *a = reinterpret_cast<const bf16*>(A), *w = reinterpret_cast<const bf16*>(W);
+  if (K == 768) skinny_gemm_kernel<3><<<grid, SK_THREADS, smem, s>>>(a, lda, w, ldw, bias, out, ldo, M, N);
+  else skinny_gemm_kernel<12><<<grid, SK_THREADS, smem, s>>>(a, lda, w, ldw, bias, out, ldo, M, N);
+  return check_launch("skinny_gemm_kernel");
 }

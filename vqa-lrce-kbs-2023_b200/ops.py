@@ -377,3 +377,15 @@ def bert_attention(qkv, mask, n_seq, L, n_heads=12):
     _call("lrce_bert_attention", _ptr(qkv), _ptr(mask), _ptr(out), n_seq, L, n_heads, _stream(),
           work=(f"L{L}", 4.0 * n_seq * n_heads * L * L * 64, 2.0 * qkv.numel() + 2.0 * out.numel()))
     return out
+
+
+def gemm_skinny(a, w, bias, out):
+    """out fp32 [M, N] = a bf16 [M, K] @ w bf16 [N, K].T (+ bias), K in {768, 3072}, few rows (lrce_gemm_skinny_bf16)"""
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(bias, torch.float32, "bias"); _req(out, torch.float32, "out")
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] >= K and out.shape == (M, N)
+    _call("lrce_gemm_skinny_bf16", _ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(bias), _ptr(out), out.stride(0),
+          _stream(), work=(f"skinny M{M}N{N}K{K}", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N))
+    return out

@@ -207,20 +207,20 @@ class _Plan:
                 site = lambda k: _Sites.layer(s, n, NL, k)
                 b = self._bias(n)
                 n1, n2, n3 = self._lnp(n, 1), self._lnp(n, 2), self._lnp(n, 3)
-                ops.gemm(xb, lw["wv"], b["bv"], out_fp32=True, out=t32)
+                ops.gemm_skinny(xb, lw["wv"], b["bv"], t32)
                 ops.rows_to_bf16(t32, y=self.vb, yT=(XT[n]["v"], s * R), group=64, p=p, site=site(0), seed=seed)
-                ops.gemm(self.vb, lw["wso"], b["bso"], out_fp32=True, out=t32)
+                ops.gemm_skinny(self.vb, lw["wso"], b["bso"], t32)
                 ops.add_ln(t32, x32, n1[0], n1[1], EPS, u_out=self.U[s, n, 0], y_f32=h1_32, y_bf16=h1b,
                            yT=(XT[n]["h1"], s * R), p_a=p, site_a=site(1), seed=seed)
-                ops.gemm(h1b, lw["wq"], b["bq"], out_fp32=True, out=self.Q[s, n])
+                ops.gemm_skinny(h1b, lw["wq"], b["bq"], self.Q[s, n])
                 ops.xattn_fwd(self.Q[s, n], self.kv_video, self.kv_text, n * 2 * D, R, S, s, Tv, Lt, n_cand, self.Pst[s, n], self.ctxb,
                               ctxT=(XT[n]["ctx"], s * R), p=p, site=site(2), seed=seed)
-                ops.gemm(self.ctxb, lw["wo"], b["bo"], out_fp32=True, out=t32)
+                ops.gemm_skinny(self.ctxb, lw["wo"], b["bo"], t32)
                 ops.add_ln(t32, h1_32, n2[0], n2[1], EPS, u_out=self.U[s, n, 1], y_f32=h2_32, y_bf16=h2b,
                            yT=(XT[n]["h2"], s * R), p_a=p, site_a=site(3), seed=seed)
-                ops.gemm(h2b, lw["w1"], b["b1"], out_fp32=True, out=self.F[s, n])
+                ops.gemm_skinny(h2b, lw["w1"], b["b1"], self.F[s, n])
                 ops.rows_to_bf16(self.F[s, n], y=self.gb, yT=(XT[n]["g"], s * R), mode=ops.ROWS_GELU_FWD, p=p, site=site(4), seed=seed)
-                ops.gemm(self.gb, lw["w2"], b["b2"], out_fp32=True, out=t32)
+                ops.gemm_skinny(self.gb, lw["w2"], b["b2"], t32)
                 nxt = (XT[n + 1]["x"], s * R) if n + 1 < NL else None
                 ops.add_ln(t32, h2_32, n3[0], n3[1], EPS, u_out=self.U[s, n, 2], y_f32=x32, y_bf16=xb, yT=nxt,
                            p_a=p, site_a=site(5), seed=seed)
@@ -242,23 +242,23 @@ class _Plan:
         # LN3 / FFN
         ops.ln_bwd(dx_a, dx_b, self.U[s, n, 2], n3[0], EPS, G[lp + "norm3.weight"], G[lp + "norm3.bias"], du=self.du3, dub=self.dyb,
                    dubT=(DYT["y"], s * R), p_a=p, site_a=site(5), seed=seed)
-        ops.gemm(self.dyb, lw["w2T"], None, out_fp32=True, out=self.dg32)
+        ops.gemm_skinny(self.dyb, lw["w2T"], None, self.dg32)
         ops.rows_to_bf16(self.dg32, aux=self.F[s, n], y=self.dfb, yT=(DYT["f"], s * R), mode=ops.ROWS_GELU_BWD, p=p, site=site(4),
                          seed=seed)
-        ops.gemm(self.dfb, lw["w1T"], None, out_fp32=True, out=self.g32)
+        ops.gemm_skinny(self.dfb, lw["w1T"], None, self.g32)
         # LN2 / cross attention
         ops.ln_bwd(self.du3, self.g32, self.U[s, n, 1], n2[0], EPS, G[lp + "norm2.weight"], G[lp + "norm2.bias"], du=self.du2,
                    dub=self.dob, dubT=(DYT["o"], s * R), p_a=p, site_a=site(3), seed=seed)
-        ops.gemm(self.dob, lw["woT"], None, out_fp32=True, out=self.g32)
+        ops.gemm_skinny(self.dob, lw["woT"], None, self.g32)
         ops.xattn_bwd(self.Q[s, n], self.kv_video, self.kv_text, n * 2 * D, R, S, s, Tv, Lt, n_cand, self.Pst[s, n], self.g32, self.dqb,
                       self.dkv_video, self.dkv_text[s], dqT=(DYT["q"], s * R), p=p, site=site(2), seed=seed)
-        ops.gemm(self.dqb, lw["wqT"], None, out_fp32=True, out=self.g32)
+        ops.gemm_skinny(self.dqb, lw["wqT"], None, self.g32)
         # LN1 / length-1 self-attention
         ops.ln_bwd(self.du2, self.g32, self.U[s, n, 0], n1[0], EPS, G[lp + "norm1.weight"], G[lp + "norm1.bias"], du=self.du1,
                    dub=self.dsab, dubT=(DYT["sa"], s * R), p_a=p, site_a=site(1), seed=seed)
-        ops.gemm(self.dsab, lw["wsoT"], None, out_fp32=True, out=self.g32)
+        ops.gemm_skinny(self.dsab, lw["wsoT"], None, self.g32)
         ops.rows_to_bf16(self.g32, y=self.dvb, yT=(DYT["v"], s * R), group=64, p=p, site=site(0), seed=seed)
-        ops.gemm(self.dvb, lw["wvT"], None, out_fp32=True, out=self.g32b)
+        ops.gemm_skinny(self.dvb, lw["wvT"], None, self.g32b)
         return self.du1, self.g32b
 
     def _layer_weight_grads(self, n):

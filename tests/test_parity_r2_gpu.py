@@ -130,9 +130,8 @@ def test_posembed_rejects_mismatched_shapes():
 def test_training_step_gradients_vs_reference(golden):
     """BASELINE configs[4]: gradients of the cross-entropy loss w.r.t. every encoder parameter from the hand-written
     forward + backward kernels (train.py) against the reference LRCEOpenEnded with drop_out_rate=0 (fp32 CPU autograd,
-    oracle/make_golden.py golden_grad). bf16 operands / fp32 accumulation: per-parameter norms within 4 %, every sampled entry
-    within 0.4 of the tensor's RMS entry (entries far below the RMS carry the absolute bf16 noise of the large ones), loss
-    within 5e-2."""
+    oracle/make_golden.py golden_grad). bf16 operands / fp32 accumulation: per-parameter norms within 4 %, relative L2 error of the
+    sampled entries of every tensor within 5 %, loss within 5e-2."""
     import lrce_b200
 
     g = golden["grad"]
@@ -157,14 +156,15 @@ def test_training_step_gradients_vs_reference(golden):
         gr = gr.float().cpu()
         ref = torch.from_numpy(g["g." + name])
         samp = gr.reshape(-1)[::1999]
-        rms = max(norm / gr.numel() ** 0.5, 1e-6 * tot_ref)  # typical entry size of this gradient tensor
-        e_s = (samp - ref).abs().max().item() / rms
+        # sampled entries: relative L2 error over the stride-1999 sample (tensors with fewer than 8 samples are covered by the
+        # norm check alone; gradients are heavy-tailed, so an entry-wise bound relative to the RMS would be meaningless)
+        e_s = ((samp - ref).norm() / ref.norm().clamp_min(1e-6 * tot_ref)).item() if ref.numel() >= 8 else 0.0
         e_n = abs(gr.double().norm().item() - norm) / max(norm, 1e-3 * tot_ref / 233 ** 0.5)
         sq += ((samp - ref) ** 2).sum().item()
         if max(e_s, e_n) > max(worst_norm, worst_samp):
             worst = name
         worst_norm, worst_samp = max(worst_norm, e_n), max(worst_samp, e_s)
-        assert e_n < 0.04 and e_s < 0.4, (name, e_n, e_s)
+        assert e_n < 0.04 and e_s < 0.05, (name, e_n, e_s)
     print(f"gradient parity over 233 tensors: worst norm error {worst_norm:.3e}, worst sampled-entry error {worst_samp:.3e} ({worst})")
 
 

@@ -132,23 +132,35 @@ int lrce_text_posembed_ln(const void* text, int text_fp32, const float* emb_cls,
 #define LRCE_ACT_RELU 2
 
 /* The whole summarisation-token walk of FusionTransformer.forward (fusionv3.py:41-51) plus final_fc (:195, ReLU :368) as
- * ONE persistent cooperative kernel: S segments x n_layers post-norm decoder layers on `rows` tokens, phases separated by
- * grid-wide barriers. `layer_table` is a DEVICE array of n_layers records of 16 device pointers each, in this order:
- *   bf16 sa_w[768,768] (out_proj . v_proj of the length-1 self-attention, folded), q_w[768,768] (pre-scaled by 1/8),
- *   o_w[768,768], w1[3072,768], w2[768,3072]; fp32 sa_b, q_b, o_b, b1, b2, norm1 g/b, norm2 g/b, norm3 g/b.
- * kv_video bf16 [(rows/n_cand)*S*Tv, ld_kv], kv_text bf16 [rows*Lt, ld_kv] hold K at column layer*1536 + head*64 and V at
- * +768 (one lrce_gemm_bf16 per modality). tok0 fp32 [768] = summarization_token; f_gamma/f_beta = fusion_layer_norm;
- * fc_w bf16 [ceil(n_out/8)*8, 768]; act = LRCE_ACT_*; out fp32 [rows, n_out]; tokens_tap NULL or fp32 [S, rows, 768]
- * (the token after each segment). `workspace`: lrce_encoder_walk_workspace_bytes(rows) bytes, 256-byte aligned, contents
- * don't matter. Tv + Lt <= 256. */
-size_t lrce_encoder_walk_workspace_bytes(int rows);
-/* profiling hook: the last CTA of later lrce_encoder_walk launches writes %globaltimer three times per phase (after its
- * prologue, before and after the grid barrier) into buf (device, >= 3 + 18 * S * n_layers entries); NULL switches it off. */
-int lrce_debug_walk_timing(unsigned long long* buf);
-int lrce_encoder_walk(const void* layer_table, int n_layers, const void* kv_video, const void* kv_text, int ld_kv,
-                      const float* tok0, const float* f_gamma, const float* f_beta, float eps, const void* fc_w,
-                      const float* fc_b, int n_out, int act, float* out, float* tokens_tap, void* workspace, int rows, int S,
-                      int Tv, int Lt, int n_cand, void* stream);
+ * ONE kernel of row-sharded 16-CTA clusters (csrc/encoder_walk.cu): S segments x n_layers post-norm decoder layers on `rows`
+ * tokens; every cluster owns <= 8 rows for the whole walk, streams the weights through TMA in a pre-packed order and runs the
+ * products as swap-AB tcgen05 MMAs; all exchanges are cluster-local (no grid barrier).
+ *
+ * lrce_encoder_walk_pack (once per weight version) re-tiles the decoder weights into that streaming order. `layer_table` is
+ * a DEVICE array of n_layers records of 16 device pointers to FP32 tensors, in this order:
+ *   sa_w[768,768] (out_proj . v_proj of the length-1 self-attention, folded), q_w[768,768] (pre-scaled by 1/8),
+ *   o_w[768,768], w1[3072,768], w2[768,3072]; sa_b, q_b, o_b, b1, b2, norm1 g/b, norm2 g/b, norm3 g/b.
+ * fc_w fp32 [n_out, 768], fc_b fp32 [n_out] = final_fc. `packed`: lrce_encoder_walk_pack_bytes(n_layers, n_out) bytes,
+ * 128-byte aligned; the LayerNorm in front of a product is folded into its weights and bias there (exact algebra).
+ *
+ * lrce_encoder_walk: kv_video bf16 [(rows/n_cand)*S*Tv, ld_kv], kv_text bf16 [rows*Lt, ld_kv] hold K at column
+ * layer*1536 + head*64 and V at +768 (one lrce_gemm_bf16 per modality). tok0 fp32 [768] = summarization_token;
+ * f_gamma/f_beta = fusion_layer_norm; act = LRCE_ACT_*; out fp32 [rows, n_out]; tokens_tap NULL or fp32 [S, rows, 768]
+ * (the token after each segment). Tv + Lt <= 192 (every reference config: 150 + at most 41), n_out <= 4096. */
+size_t lrce_encoder_walk_pack_bytes(int n_layers, int n_out);
+int lrce_encoder_walk_pack(const void* layer_table, int n_layers, const float* fc_w, const float* fc_b, int n_out, void* packed,
+                           void* stream);
+int lrce_encoder_walk(const void* packed, int n_layers, const void* kv_video, const void* kv_text, int ld_kv, const float* tok0,
+                      const float* f_gamma, const float* f_beta, float eps, int n_out, int act, float* out, float* tokens_tap,
+                      int rows, int S, int Tv, int Lt, int n_cand, void* stream);
+/* Instrumented instantiation of the same kernel for tools/ (no library-side state: everything is a per-call argument):
+ * prof = device int64 [CTAs][32] receiving the cycles thread 0 of each CTA spent per sub-step of the dependency chain;
+ * max_clusters > 0 caps the number of clusters; variant = 1 runs the production code, other values select code variants kept
+ * for same-box A/B measurements. */
+int lrce_encoder_walk_profile(const void* packed, int n_layers, const void* kv_video, const void* kv_text, int ld_kv,
+                              const float* tok0, const float* f_gamma, const float* f_beta, float eps, int n_out, int act,
+                              float* out, float* tokens_tap, int rows, int S, int Tv, int Lt, int n_cand, void* stream,
+                              long long* prof, int max_clusters, int variant);
 
 /* ---- row / sequence kernels: BERT-base (text.py:5-17) and the encoder's training step (configs[4]) ----------------------
  * Dropout arguments: p (0 = off), a site id and a seed; the mask of element i is a counter-based hash of (seed, site, i), so

@@ -24,6 +24,11 @@ needs_ref = pytest.mark.skipif(ref_harness.find_reference() is None, reason="no 
 CFG = dict(feature_dim=768, video_feature_res=[7, 7], video_feature_dim=1024, frame_sample_size=5, temporal_scale=[3])
 
 
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
 @pytest.fixture(scope="module")
 def nccl_single_rank():
     import torch.distributed as dist
@@ -92,7 +97,8 @@ def test_reference_agent_oe_eval_train_checkpoint(golden, tmp_path, nccl_single_
     y = seen[0]
     order = [int(((y[i][None] - ref).abs().amax(-1)).argmin()) for i in range(2)]  # DistributedSampler shuffles
     assert sorted(order) == [0, 1]
-    assert (y - ref[order]).abs().max().item() < 0.12
+    # relative norm 1.5 x measured (8e-3); the max over 2000 logits is an extreme-value statistic (0.10 .. 0.15 across builds)
+    assert rel_l2(y, ref[order]) < 1.2e-2 and (y - ref[order]).abs().max().item() < 0.2
     assert abs(float(ev.last_metric_val) - 1.0) < 1e-6      # accuracy against the reference's own top-1: 100 %
     assert np.isfinite(ev.last_loss)
 
@@ -153,4 +159,4 @@ def test_reference_agent_mc_eval(golden, tmp_path, nccl_single_rank):
     h.remove()
     y = seen[0]
     order = [int(((y[i][None] - ref).abs().amax(-1)).argmin()) for i in range(2)]
-    assert sorted(order) == [0, 1] and (y - ref[order]).abs().max().item() < 0.12
+    assert sorted(order) == [0, 1] and (y - ref[order]).abs().max().item() < 0.06  # (2, 5) logits of magnitude ~5: measured 0.033

@@ -15,6 +15,9 @@ import weights as W  # noqa: E402
 CFG = dict(feature_dim=768, video_feature_res=[7, 7], video_feature_dim=1024, frame_sample_size=5, temporal_scale=[3])
 
 
+# tolerances = 1.5 x measured (features 9.0e-3, logit rel-L2 8e-3); see test_msvd_b2_vs_reference for the max-abs bound
+FEAT_TOL, LOGIT_TOL, LOGIT_REL_TOL = 1.4e-2, 0.2, 1.2e-2
+
 def build(kind, ncls, L):
     import lrce_b200
 
@@ -44,13 +47,16 @@ def test_msvd_b2_vs_reference(golden, msvd):
     assert y.dtype == torch.float32 and y.shape == (2, 1000)
     for k in ("patch_embed", "stage0.out", "stage1.out", "stage2.out"):
         err = rel_l2(taps[k].reshape(-1)[::997], torch.from_numpy(g[f"msvd-qa-oe.{k}.sample"]))
-        assert err < 3e-2, (k, err)
+        assert err < FEAT_TOL, (k, err)
     err = rel_l2(feats.reshape(-1)[::997], torch.from_numpy(g["msvd-qa-oe.video_features.sample"]))
-    assert err < 3e-2, err
+    assert err < FEAT_TOL, err  # measured 9.0e-3
     ref = torch.from_numpy(g["msvd-qa-oe.logits"])
     d = (y.cpu() - ref).abs().max().item()
-    print("msvd b2: feature rel_l2", err, "logit max abs", d, "rel_l2", rel_l2(y, ref))
-    assert d < 0.25, d
+    r = rel_l2(y, ref)
+    print("msvd b2: feature rel_l2", err, "logit max abs", d, "rel_l2", r)
+    # measured: rel-L2 7.9e-3 .. 8.5e-3; the maximum over 2000 logits of std ~4 is an extreme-value statistic (0.10 .. 0.15
+    # between kernel builds of identical rel-L2), so the relative norm carries the tight bound
+    assert r < LOGIT_REL_TOL and d < LOGIT_TOL, (r, d)
     assert torch.equal(y.cpu().argmax(-1), ref.argmax(-1))
 
 
@@ -64,7 +70,7 @@ def test_mc_count_b2_vs_reference(golden, name, kind, ncls, L):
     assert y.shape == ref.shape
     d = (y.cpu() - ref).abs().max().item()
     print(name, "max abs", d, y.cpu().tolist(), ref.tolist())
-    assert d < 0.25, d
+    assert d < 0.06, d  # measured 0.025 .. 0.034 on logits of magnitude ~5
 
 
 def test_msvd_b32_batch_invariance(golden, msvd):
@@ -77,7 +83,7 @@ def test_msvd_b32_batch_invariance(golden, msvd):
     ref = torch.from_numpy(golden["e2e"]["msvd-qa-oe.logits"])
     assert y.shape == (32, 1000)
     y = y.cpu().view(16, 2, 1000)
-    assert (y - ref[None]).abs().max().item() < 0.25
+    assert (y - ref[None]).abs().max().item() < LOGIT_TOL and rel_l2(y, ref[None].expand(16, 2, 1000)) < LOGIT_REL_TOL
     assert torch.equal(y.argmax(-1), ref.argmax(-1)[None].expand(16, 2))
     assert (y - y[:1]).abs().max().item() < 1e-3  # same kernels, same data -> same answer wherever the clip sits
 

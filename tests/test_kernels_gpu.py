@@ -287,3 +287,54 @@ def test_fusion_heads_vs_reference_golden(golden, name, kind, ncls, L):
         # (0.02 here), so the chosen class must be one whose reference logit is within 2 x tolerance of the maximum
         picked = ref.gather(1, y.cpu().argmax(-1, keepdim=True)).squeeze(1)
         assert (ref.max(-1).values - picked).max().item() < 0.3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# lrce_encoder_walk_pack: the streaming order of the decoder weights is index work -> bit-exact against a torch re-tiling
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_out", [1000, 1500, 1])
+def test_encoder_walk_pack_layout(ops, n_out):
+    L, d, CL = 2, 768, 16
+    gen = torch.Generator().manual_seed(7)
+    rnd = lambda *s: torch.randn(*s, generator=gen)
+    names = ("sa_w", "q_w", "o_w", "w1", "w2", "sa_b", "q_b", "o_b", "b1", "b2", "n1g", "n1b", "n2g", "n2b", "n3g", "n3b")
+    shapes = dict(sa_w=(d, d), q_w=(d, d), o_w=(d, d), w1=(4 * d, d), w2=(d, 4 * d), b1=(4 * d,))
+    layers = [{k: rnd(*shapes.get(k, (d,))).cuda() for k in names} for _ in range(L)]
+    fc_w, fc_b = rnd(n_out, d).cuda(), rnd(n_out).cuda()
+    table = torch.tensor([[lw[k].data_ptr() for k in names] for lw in layers], dtype=torch.int64, device="cuda")
+    packed = ops.encoder_walk_pack(table, L, fc_w, fc_b, n_out)
+    torch.cuda.synchronize()
+    mt = ((n_out + CL - 1) // CL + 63) // 64
+    w_rows, head_rows = L * CL * 6336, CL * mt * 768
+    stream = packed[: (w_rows + head_rows) * 128].view(torch.bfloat16).view(-1, 64)
+
+    def tiles48(W):  # [768, 768] -> [rank][k-block][48 rows][64]
+        return W.view(CL, 48, 12, 64).permute(0, 2, 1, 3).reshape(CL, 576, 64)
+
+    for n, lw in enumerate(layers):
+        sa = lw["sa_w"] * (layers[n - 1]["n3g"] if n > 0 else 1.0)  # LayerNorm gamma of the norm in front, folded
+        q = lw["q_w"] * lw["n1g"]
+        w1 = (lw["w1"] * lw["n2g"]).view(CL, 192, 12, 64).permute(0, 2, 1, 3).reshape(CL, 2304, 64)
+        w2 = lw["w2"].view(12, 64, CL, 3, 64).permute(2, 0, 3, 1, 4).reshape(CL, 2304, 64)
+        want = torch.cat([tiles48(sa), tiles48(q), tiles48(lw["o_w"]), w1, w2], 1).bfloat16()
+        got = stream[n * CL * 6336:(n + 1) * CL * 6336].view(CL, 6336, 64)
+        assert torch.equal(got, want), n
+    fc_pad = torch.zeros(CL * 64 * mt, d, device="cuda")
+    fc_pad[:n_out] = fc_w
+    want = fc_pad.view(CL * mt, 64, 12, 64).permute(0, 2, 1, 3).reshape(-1, 64).bfloat16()
+    assert torch.equal(stream[w_rows:], want)
+    # parameter blocks: biases with the folded beta term (b + W beta), LayerNorm slices, tail, head bias
+    off = (w_rows + head_rows) * 128
+    params = packed[off: off + L * CL * 672 * 4].view(torch.float32).view(L, CL, 672)
+    tail = packed[off + L * CL * 672 * 4:][: 2 * d * 4].view(torch.float32).view(2, d)
+    hbias = packed[off + L * CL * 672 * 4 + 2 * d * 4:].view(torch.float32)
+    for n, lw in enumerate(layers):
+        sa_b = lw["sa_b"] + (lw["sa_w"].double() @ layers[n - 1]["n3b"].double()).float() if n > 0 else lw["sa_b"]
+        q_b = lw["q_b"] + (lw["q_w"].double() @ lw["n1b"].double()).float()
+        b1 = lw["b1"] + (lw["w1"].double() @ lw["n2b"].double()).float()
+        sl = lambda v: v.view(CL, 48)
+        want = torch.cat([sl(sa_b), sl(q_b), sl(lw["o_b"]), sl(lw["b2"]), sl(lw["n1g"]), sl(lw["n1b"]), sl(lw["n2g"]), sl(lw["n2b"]),
+                          sl(lw["n3g"]), sl(lw["n3b"]), b1.view(CL, 192)], 1)
+        assert torch.allclose(params[n], want, rtol=1e-5, atol=2e-4), (n, (params[n] - want).abs().max().item())
+    assert torch.equal(tail[0], layers[-1]["n3g"]) and torch.equal(tail[1], layers[-1]["n3b"])
+    assert torch.equal(hbias[:n_out], fc_b) and not hbias[n_out:].any()

@@ -1,5 +1,4 @@
-"""GPU probe: timing of the encoder (K/V GEMMs + persistent token walk) and, through the lrce_debug_walk_timing hook,
-the per-phase breakdown of the walk kernel as seen by CTA 0 (work time vs grid-barrier wait per phase)."""
+"""GPU probe: timing of the encoder (projection + pos-embeds + K/V GEMMs + the cluster-sharded token walk), per launch."""
 import os
 import sys
 
@@ -38,24 +37,3 @@ with torch.no_grad():
     tr, ops.trace = ops.trace, None
     for name, tag, fl, by, a, b in tr:
         print(f"  {name:28s} {tag:24s} {a.elapsed_time(b)*1e3:8.1f} us")
-    n = 3 + 18 * S * 12
-    buf = torch.zeros(n, dtype=torch.int64, device="cuda")
-    _lib.check(_lib.lib().lrce_debug_walk_timing(buf.data_ptr()), "timing hook")
-    m(vf, tf)
-    torch.cuda.synchronize()
-    _lib.lib().lrce_debug_walk_timing(0)
-t = buf.cpu().tolist()
-names = ["P1 self", "P2 q", "P3 attn", "P4 out", "P5 fc1", "P6 fc2"]
-pro, work, wait = [0.0] * 6, [0.0] * 6, [0.0] * 6
-# stamps: [start] then per phase (after prologue / staging, before barrier, after barrier)
-for i in range(S * 12 * 6):
-    prev = t[3 * i]  # after the previous barrier (or kernel start)
-    a, done, released = t[3 * i + 1], t[3 * i + 2], t[3 * i + 3]
-    pro[i % 6] += a - prev
-    work[i % 6] += done - a
-    wait[i % 6] += released - done
-k = S * 12
-for j in range(6):
-    print(f"  {names[j]:8s} prologue {pro[j]/k/1e3:6.2f} us  tiles {work[j]/k/1e3:6.2f} us  barrier wait {wait[j]/k/1e3:6.2f} us"
-          f"   (CTA 1, mean over {k} layer-steps)")
-print(f"  head     {(t[-1]-t[-3])/1e3:7.2f} us ; whole walk {(t[-1]-t[0])/1e3:8.1f} us")

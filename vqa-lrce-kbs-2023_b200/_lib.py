@@ -28,10 +28,11 @@ _SIGNATURES = {
     "lrce_window_attention_bf16": [_vp, _vp, _vp] + [_i] * 8 + [_vp],
     "lrce_video_posembed_ln": [_vp] * 7 + [_f, _vp, _i, _i, _i, _i, _vp],
     "lrce_text_posembed_ln": [_vp, _i] + [_vp] * 4 + [_f, _vp, _i, _i, _vp],
-    "lrce_encoder_walk_workspace_bytes": [_i],
-    "lrce_debug_walk_timing": [_vp],
+    "lrce_encoder_walk_pack_bytes": [_i, _i],
+    "lrce_encoder_walk_pack": [_vp, _i, _vp, _vp, _i, _vp, _vp],
     "lrce_debug_attention_timing": [_vp],
-    "lrce_encoder_walk": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "lrce_encoder_walk": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "lrce_encoder_walk_profile": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i],
     "lrce_add_ln_768": [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _i, _f, _i, _u64, _vp, _vp],
     "lrce_ln_bwd_768": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _ll, _f, _i, _f, _i, _u64, _vp, _vp],
     "lrce_rows_f32_to_bf16": [_vp, _vp, _vp, _vp, _i, _i, _ll, _i, _i, _i, _f, _i, _u64, _vp, _vp],
@@ -47,7 +48,7 @@ _SIGNATURES = {
     "lrce_bert_embed_ln": [_vp] * 7 + [_f, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "lrce_bert_attention": [_vp, _vp, _vp, _i, _i, _i, _vp],
 }
-_RESTYPES = {"lrce_last_error": _c.c_char_p, "lrce_encoder_walk_workspace_bytes": _c.c_size_t}
+_RESTYPES = {"lrce_last_error": _c.c_char_p, "lrce_encoder_walk_pack_bytes": _c.c_size_t}
 
 _lib = None
 

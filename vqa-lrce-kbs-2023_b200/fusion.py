@@ -8,9 +8,10 @@ Execution plan of one forward (eval semantics — dropouts are identities, fusio
      ([Wk;Wv] of the 12 layers concatenated -> N = 18432). Text rows are projected once, not once per segment, and for
      multiple choice the video rows are projected once per clip, not once per candidate (fusionv3.py:259 expands them).
   4. the summarisation token: S x 12 layer-steps of 6 dependent sub-steps plus final_fc (ReLU fused for the counting
-     head, fusionv3.py:368) run as ONE persistent cooperative kernel with grid-wide barriers between sub-steps (see
-     csrc/encoder_walk.cu). Self-attention over a length-1 target is softmax over a single key = 1, so it reduces to
-     out_proj(v_proj(x)); the two matrices are folded into one 768x768 product at pack time.
+     head, fusionv3.py:368) run as ONE kernel of row-sharded 16-CTA clusters (csrc/encoder_walk.cu): the decoder weights
+     are re-tiled once per weight version into the order each CTA streams them (lrce_encoder_walk_pack). Self-attention
+     over a length-1 target is softmax over a single key = 1, so it reduces to out_proj(v_proj(x)); the two matrices are
+     folded into one 768x768 product at pack time.
 """
 from typing import Iterable, List
 
@@ -116,6 +117,7 @@ class LRCEOpenEnded(_PackedModule):
             t_b=f32(te.layer_norm.bias), tok=f32(ft.summarization_token.reshape(1, d)),
             f_g=f32(ft.fusion_layer_norm.weight), f_b=f32(ft.fusion_layer_norm.bias),
             fc_w=bf(pad8(self.final_fc.weight.detach().float())), fc_b=f32(self.final_fc.bias), layers=[])
+        walk_rows = []  # fp32 masters for lrce_encoder_walk_pack (the bf16 copies in pk["layers"] feed the training kernels)
         if hasattr(self, "projection_layer"):
             pk["proj_w"], pk["proj_b"] = bf(self.projection_layer.weight), f32(self.projection_layer.bias)
         kv_w, kv_b = [], []
@@ -124,6 +126,11 @@ class LRCEOpenEnded(_PackedModule):
             so_w, so_b = lyr.self_attn.out_proj.weight.detach().double(), lyr.self_attn.out_proj.bias.detach().double()
             ca_w, ca_b = lyr.multihead_attn.in_proj_weight.detach().float(), lyr.multihead_attn.in_proj_bias.detach().float()
             scale = (d // 12) ** -0.5
+            walk_rows.append([f32((so_w @ sa_w[2 * d:]).float()), f32(ca_w[:d] * scale), f32(lyr.multihead_attn.out_proj.weight),
+                              f32(lyr.linear1.weight), f32(lyr.linear2.weight), f32((so_w @ sa_b[2 * d:] + so_b).float()),
+                              f32(ca_b[:d] * scale), f32(lyr.multihead_attn.out_proj.bias), f32(lyr.linear1.bias),
+                              f32(lyr.linear2.bias), f32(lyr.norm1.weight), f32(lyr.norm1.bias), f32(lyr.norm2.weight),
+                              f32(lyr.norm2.bias), f32(lyr.norm3.weight), f32(lyr.norm3.bias)])
             pk["layers"].append(dict(
                 # length-1 self-attention == out_proj(v_proj(x)): fold the two linears (exact algebra, fp64 product)
                 sa_w=bf((so_w @ sa_w[2 * d:]).float()), sa_b=f32((so_w @ sa_b[2 * d:] + so_b).float()),
@@ -135,11 +142,12 @@ class LRCEOpenEnded(_PackedModule):
             kv_w.append(ca_w[d:])
             kv_b.append(ca_b[d:])
         pk["kv_w"], pk["kv_b"] = bf(torch.cat(kv_w)), f32(torch.cat(kv_b))  # [12*1536, 768]: layer-major, [k | v]
-        # device table of per-layer pointers in the order lrce_encoder_walk documents (include/lrce_b200.h)
-        order = ("sa_w", "q_w", "o_w", "w1", "w2", "sa_b", "q_b", "o_b", "b1", "b2")
-        rows = [[lw[k].data_ptr() for k in order] + [t.data_ptr() for n in ("n1", "n2", "n3") for t in lw[n]]
-                for lw in pk["layers"]]
-        pk["layer_table"] = torch.tensor(rows, dtype=torch.int64, device=dev)
+        # device table of per-layer pointers in the order lrce_encoder_walk_pack documents (include/lrce_b200.h); the fp32
+        # masters are only needed until the pack kernels have run
+        table = torch.tensor([[t.data_ptr() for t in row] for row in walk_rows], dtype=torch.int64, device=dev)
+        pk["walk_packed"] = ops.encoder_walk_pack(table, len(walk_rows), f32(self.final_fc.weight), pk["fc_b"],
+                                                  self.final_fc.out_features)
+        torch.cuda.current_stream(dev).synchronize()
         return pk
 
     def _validate(self, video_features, text_features, n_cand):
@@ -185,23 +193,22 @@ class LRCEOpenEnded(_PackedModule):
         ops.gemm(temb.view(Bq * Lt, d), pk["kv_w"], pk["kv_b"], out=st["kv_text"])
         out = torch.empty((Bq, n_out), device=dev, dtype=torch.float32)
         tap = torch.empty((S, Bq, d), device=dev, dtype=torch.float32) if taps is not None else None
-        ops.encoder_walk(pk["layer_table"], len(pk["layers"]), st["kv_video"], st["kv_text"], pk["tok"], pk["f_g"], pk["f_b"],
-                         EPS, pk["fc_w"], pk["fc_b"], n_out, act, out, st["ws"], Bq, S, Tv, Lt, n_cand, tokens_tap=tap)
+        ops.encoder_walk(pk["walk_packed"], len(pk["layers"]), st["kv_video"], st["kv_text"], pk["tok"], pk["f_g"], pk["f_b"],
+                         EPS, n_out, act, out, Bq, S, Tv, Lt, n_cand, tokens_tap=tap)
         if taps is not None:
             for s in range(S):
                 taps[f"token.s{s}"] = tap[s]
         return out
 
     def _token_state(self, pk, dev, B, Bq, S, Tv, Lt):
-        """K/V buffers and the walk's workspace for one problem shape (reused across forwards)"""
+        """K/V buffers for one problem shape (reused across forwards)"""
         key = (dev, B, Bq, S, Tv, Lt)
         st = self._states.get(key)
         if st is None:
             if len(self._states) > 8:
                 self._states.clear()
             h = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
-            st = dict(kv_video=h(B * S * Tv, pk["kv_w"].shape[0]), kv_text=h(Bq * Lt, pk["kv_w"].shape[0]),
-                      ws=ops.encoder_walk_workspace(Bq, dev))
+            st = dict(kv_video=h(B * S * Tv, pk["kv_w"].shape[0]), kv_text=h(Bq * Lt, pk["kv_w"].shape[0]))
             self._states[key] = st
         return st
 

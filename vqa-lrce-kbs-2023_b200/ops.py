@@ -209,26 +209,29 @@ def text_posembed_ln(text, emb_cls, emb_pos, gamma, beta, eps, out=None):
     return out
 
 
-def encoder_walk_workspace(rows, device):
-    """scratch for encoder_walk (contents don't matter; the library zeroes its barrier word itself)"""
-    n = _lib.lib().lrce_encoder_walk_workspace_bytes(int(rows))
-    return torch.empty((n + 255) // 256 * 256, device=device, dtype=torch.uint8)
-
-
-def encoder_walk(layer_table, n_layers, kv_video, kv_text, tok0, f_g, f_b, eps, fc_w, fc_b, n_out, act, out, workspace, rows,
-                 S, Tv, Lt, n_cand, tokens_tap=None):
-    """the whole summarisation-token walk + answer head as one persistent cooperative kernel (lrce_encoder_walk)"""
-    _req(kv_video, torch.bfloat16, "kv_video"); _req(kv_text, torch.bfloat16, "kv_text"); _req(fc_w, torch.bfloat16, "fc_w")
-    _req(tok0, torch.float32, "tok0"); _req(out, torch.float32, "out"); _req(tokens_tap, torch.float32, "tokens_tap")
+def encoder_walk_pack(layer_table, n_layers, fc_w, fc_b, n_out):
+    """decoder weights (fp32 masters, 16 device pointers per layer) -> the walk's per-CTA streaming order (lrce_encoder_walk_pack)"""
+    _req(fc_w, torch.float32, "fc_w"); _req(fc_b, torch.float32, "fc_b")
     assert layer_table.dtype == torch.int64 and layer_table.is_cuda and layer_table.shape == (n_layers, 16)
+    assert fc_w.is_contiguous() and fc_w.shape == (n_out, 768) and fc_b.shape == (n_out,)
+    n = _lib.lib().lrce_encoder_walk_pack_bytes(int(n_layers), int(n_out))
+    packed = torch.empty(n, device=fc_w.device, dtype=torch.uint8)
+    assert packed.data_ptr() % 128 == 0
+    _call("lrce_encoder_walk_pack", _ptr(layer_table), n_layers, _ptr(fc_w), _ptr(fc_b), n_out, _ptr(packed), _stream())
+    return packed
+
+
+def encoder_walk(packed, n_layers, kv_video, kv_text, tok0, f_g, f_b, eps, n_out, act, out, rows, S, Tv, Lt, n_cand,
+                 tokens_tap=None):
+    """the whole summarisation-token walk + answer head as one kernel of row-sharded 16-CTA clusters (lrce_encoder_walk)"""
+    _req(kv_video, torch.bfloat16, "kv_video"); _req(kv_text, torch.bfloat16, "kv_text"); _req(packed, torch.uint8, "packed")
+    _req(tok0, torch.float32, "tok0"); _req(out, torch.float32, "out"); _req(tokens_tap, torch.float32, "tokens_tap")
     assert kv_video.stride(0) == kv_text.stride(0) and out.is_contiguous() and out.shape == (rows, n_out)
-    assert fc_w.shape[0] % 8 == 0 and fc_w.shape[0] >= n_out and fc_w.shape[1] == 768
-    assert workspace.data_ptr() % 256 == 0 and workspace.numel() >= _lib.lib().lrce_encoder_walk_workspace_bytes(int(rows))
+    assert packed.numel() == _lib.lib().lrce_encoder_walk_pack_bytes(int(n_layers), int(n_out))
     if tokens_tap is not None:
         assert tokens_tap.is_contiguous() and tokens_tap.shape == (S, rows, 768)
-    _call("lrce_encoder_walk", _ptr(layer_table), n_layers, _ptr(kv_video), _ptr(kv_text), kv_video.stride(0), _ptr(tok0),
-          _ptr(f_g), _ptr(f_b), float(eps), _ptr(fc_w), _ptr(fc_b), n_out, act, _ptr(out), _ptr(tokens_tap), _ptr(workspace),
-          rows, S, Tv, Lt, n_cand, _stream(),
+    _call("lrce_encoder_walk", _ptr(packed), n_layers, _ptr(kv_video), _ptr(kv_text), kv_video.stride(0), _ptr(tok0),
+          _ptr(f_g), _ptr(f_b), float(eps), n_out, act, _ptr(out), _ptr(tokens_tap), rows, S, Tv, Lt, n_cand, _stream(),
           work=(f"R{rows}S{S}", 2.0 * rows * S * n_layers * (4 * 768 * 768 + 2 * 768 * 3072 + 2 * (Tv + Lt) * 768),
                 2.0 * S * n_layers * (3 * 768 * 768 + 2 * 768 * 3072) + 2.0 * rows * S * n_layers * (Tv + Lt) * 1536 * 2))
     return out

@@ -127,6 +127,17 @@ int lrce_video_posembed_ln(const void* proj, const float* emb_cls, const float* 
 int lrce_text_posembed_ln(const void* text, int text_fp32, const float* emb_cls, const float* emb_pos, const float* gamma,
                           const float* beta, float eps, void* out, int Bt, int L, void* stream);
 
+/* The Swin MLP block of the stage-1 blocks (C = 128) as ONE kernel (csrc/mlp_fused.cu):
+ *   out = x + fc2( gelu( fc1( LayerNorm(x) ) ) )        video_swin_ori.py:40-57 (Mlp), :284-285 and :304 (norm2, residual)
+ * The hidden activations [M, 512] never leave the SM. x bf16 [M, ldx] raw rows; the LayerNorm is folded exactly as in
+ * lrce_gemm_bf16: w1 bf16 [512, 128] = W1 diag(gamma), b1 = b + W1 beta, colsum1[n] = sum_k w1[n, k], in_stats = float2
+ * [M][4] (mean, M2) partials of the four 32-column chunks of every row (the out_stats of the GEMM that produced x).
+ * w2 bf16 [128, 512], b2 fp32 [128]. out bf16 [M, ldo] may alias x. out_stats NULL or float2 [M][4] partials of the rows
+ * written (for the next block's folded norm1). Replaces two lrce_gemm_bf16 calls (EPI_BIAS_GELU + EPI_BIAS_RESIDUAL). */
+int lrce_mlp_fused_bf16(const void* x, int ldx, const void* w1, const float* b1, const float* colsum1, const float* in_stats,
+                        float in_eps, const void* w2, const float* b2, void* out, int ldo, float* out_stats, int M, int C,
+                        void* stream);
+
 #define LRCE_ACT_NONE 0
 #define LRCE_ACT_GELU 1
 #define LRCE_ACT_RELU 2

@@ -127,6 +127,36 @@ def test_gemm_emits_row_statistics(ops, M, N, K, epi):
     assert ((got[..., 1] - want[..., 1]).abs() / want[..., 1].clamp_min(1e-3)).max().item() < 2e-2
 
 
+@pytest.mark.parametrize("M", [128, 300, 4097, 148 * 128 * 2 + 77])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_mlp_fused_vs_two_gemms_and_torch(ops, M, inplace):
+    """lrce_mlp_fused_bf16 (video_swin_ori.py:40-57, :284-285, :304) == x + fc2(gelu(fc1(LN(x)))) in fp32, and == the two-GEMM
+    path it replaces up to the bf16 rounding of the hidden activations; row statistics of the result as the GEMMs emit them"""
+    C = 128
+    x = (seeded((M, C), 11, 1.5) + 0.4).bfloat16().cuda()
+    w1, b1 = seeded((4 * C, C), 12, 0.06).cuda(), seeded((4 * C,), 13, 0.3).cuda()
+    w2, b2 = seeded((C, 4 * C), 14, 0.06).cuda(), seeded((C,), 15, 0.3).cuda()
+    g, beta = (1 + 0.2 * seeded((C,), 16)).cuda(), (0.2 * seeded((C,), 17)).cuda()
+    ref = x.float() + torch.nn.functional.gelu(torch.nn.functional.layer_norm(x.float(), (C,), g, beta, 1e-5) @ w1.t() + b1) @ w2.t() + b2
+    wg = (w1.double() * g.double()[None]).bfloat16()
+    colsum = wg.double().sum(1).float()
+    bias1 = (b1.double() + w1.double() @ beta.double()).float()
+    st_in = chunk_stats(x)
+    hid = ops.gemm(x, wg, bias1, epilogue=ops.EPI_BIAS_GELU, ln_in=(st_in, colsum, 1e-5))
+    st_two = torch.zeros(M * 4 * 2, device="cuda")
+    two = ops.gemm(hid, w2.bfloat16(), b2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, stats_out=st_two)
+    st = torch.zeros(M * 4 * 2, device="cuda")
+    xin = x.clone()
+    y = ops.mlp_fused(xin, wg, bias1, colsum, st_in, 1e-5, w2.bfloat16(), b2, out=xin if inplace else None, stats_out=st)
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < 6e-3, rel_l2(y, ref)
+    assert rel_l2(y, two) < 4e-3, rel_l2(y, two)
+    want = chunk_stats(y)
+    got = st.view(M, 4, 2)
+    assert (got[..., 0] - want[..., 0]).abs().max().item() < 2e-3 * max(1.0, y.float().abs().max().item())
+    assert ((got[..., 1] - want[..., 1]).abs() / want[..., 1].clamp_min(1e-3)).max().item() < 2e-2
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # row kernels
 # ------------------------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ _SIGNATURES = {
     "lrce_abi_version": [],
     "lrce_last_error": [],
     "lrce_gemm_bf16": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp, _f, _vp, _vp],
+    "lrce_mlp_fused_bf16": [_vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "lrce_layernorm_bf16": [_vp, _vp, _vp, _vp, _f, _ll, _i, _i, _vp],
     "lrce_patch_merge_ln_bf16": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp],
     "lrce_patch_gather_f32": [_vp, _vp, _i, _i, _i, _i, _vp],

@@ -146,31 +146,6 @@ __device__ __forceinline__ void tmem_ld_8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr)
                : "memory");
 }
-// One lane of the (converged) warp; the MMA warp keeps its control flow warp-uniform and only the tcgen05 instructions sit
-// behind this predicate, so descriptor arithmetic stays on the uniform datapath instead of a per-lane waterfall loop.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-  return pred != 0;
-}
-// K-major SWIZZLE_128B operand descriptor = {lo, hi}: hi is constant (SBO 1024 B, version 1, layout 2), lo = (address >> 4)
-// | LBO 1; operands that differ only in their start address differ only in lo, by (byte offset >> 4).
-constexpr uint32_t WK_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | 0x10000u; }
-template <bool ACC>
-__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 da, db;\n"
-      "mov.b64 da, {%1, %4};\n"
-      "mov.b64 db, {%2, %4};\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(WK_DESC_HI), "n"(ACC ? 1 : 0)
-      : "memory");
-}
 // position in the slot ring: slot index and the parity of its current use (no divisions on the per-slot paths)
 struct RingPos {
   uint32_t s, ph;

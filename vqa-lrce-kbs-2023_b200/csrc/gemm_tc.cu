@@ -48,20 +48,27 @@ struct GemmParams {
                      // rounding noise shifts the mean by ~2^-9 rms / sqrt(cw), far below bf16)
 };
 
+// does this configuration stage its residual tile through TMA? (see GemmCfg)
+constexpr bool gemm_res_tma(int BN, int EPI, int CG) { return EPI == 2 /*EPI_BIAS_RESIDUAL*/ && (CG == 2 || BN == 128); }
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 640;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, row-statistics; warps 4-19: epilogue
 constexpr int GEMM_EPI_WARPS = 16;  // four per TMEM lane quarter, each owning a quarter of the tile's columns
 
-template <int BN, int CG>
+// RES: the residual tile of the EPI_BIAS_RESIDUAL epilogue (this CTA's 128 rows x BN columns) is staged in shared memory by
+// TMA a tile ahead of its use (CTA pairs and 128-wide tiles; the 128 x 256 single-CTA tiles have no room for it)
+template <int BN, int CG, bool RES = false>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : (RES ? 4 : 6);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;  // a CTA pair splits the B tile between its two CTAs
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
   static constexpr int SLAB_BYTES = 32 * 32 * 2;  // one epilogue warp's 32-row x 32-column bf16 output slab (64B-swizzled)
   static constexpr int RN_BYTES = 2 * GEMM_BM * 8;  // (rstd, -rstd*mean) of the rows of two tiles in flight
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + GEMM_EPI_WARPS * SLAB_BYTES + RN_BYTES + 256 /*barriers*/;
+  static constexpr int RES_BYTES = RES ? GEMM_BM * BN * 2 : 0;  // BN / 32 column pieces of 128 rows x 64 B, 64B-swizzled
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + GEMM_EPI_WARPS * SLAB_BYTES + RES_BYTES + RN_BYTES + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "GEMM shared-memory budget");
 };
 
 // erf-GELU (nn.GELU default, video_swin_ori.py:42) as 0.5 x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form
@@ -244,10 +251,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int ro
 template <int BN, int EPI, typename OutT, bool LNIN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   constexpr bool TMA_STORE = (sizeof(OutT) == 2) && (EPI != EPI_BIAS_LN);
   static_assert(CG == 1 || (CG == 2 && TMA_STORE), "CTA pairs are used with the TMA-store epilogues only");
-  using Cfg = GemmCfg<BN, CG>;
+  constexpr bool RES_TMA = gemm_res_tma(BN, EPI, CG);
+  using Cfg = GemmCfg<BN, CG, RES_TMA>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int WCOLS = BN / 4;      // columns of the tile owned by one epilogue warp
   constexpr int PIECES = WCOLS / 32;  // 32-column pieces per warp and tile
@@ -257,14 +265,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* sC = sB + STAGES * Cfg::B_BYTES;  // 16 per-warp output slabs (stage sizes are multiples of 1024)
-  float2* s_rn = reinterpret_cast<float2*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES);
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES + Cfg::RN_BYTES);
+  uint8_t* sRes = sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES;  // residual tile (RES_TMA), 512-byte aligned pieces
+  float2* s_rn = reinterpret_cast<float2*>(sRes + Cfg::RES_BYTES);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sRes + Cfg::RES_BYTES + Cfg::RN_BYTES);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint64_t* bar_rnfull = bar_tempty + 2;
   uint64_t* bar_rnempty = bar_rnfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_rnempty + 2);
+  uint64_t* bar_resfull = bar_rnempty + 2;
+  uint64_t* bar_resempty = bar_resfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_resempty + 1);
   // LayerNorm epilogue scratch [tile parity][column quarter][sum | sumsq][row] aliases the (then unused) output slabs
   float* ln_part = reinterpret_cast<float*>(sC);
 
@@ -285,6 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (TMA_STORE) tma_prefetch_desc(&tmC);
+    if (RES_TMA) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -297,6 +309,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&bar_rnfull[a], 1);
       mbar_init(&bar_rnempty[a], GEMM_EPI_WARPS);
     }
+    mbar_init(bar_resfull, 1);
+    mbar_init(bar_resempty, GEMM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -312,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, rit = 0;
       uint32_t phase = 0;
       for (int t = unit; t < n_tiles; t += n_units) {
         const int m0 = (t / n_tiles_n) * (GEMM_BM * CG) + row_off;
@@ -330,6 +344,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &bar_full[stage], kb * GEMM_BK, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (RES_TMA) {
+          // this tile's residual rows: the buffer is free once every epilogue warp has read the previous tile's rows; the
+          // load then has the rest of this tile's main loop to land (own shared memory and barrier, also in a CTA pair)
+          mbar_wait_parked(bar_resempty, (rit & 1) ^ 1);
+          mbar_expect_tx(bar_resfull, Cfg::RES_BYTES);
+#pragma unroll
+          for (int pc = 0; pc < BN / 32; ++pc) tma_load_2d(sRes + pc * (GEMM_BM * 64), &tmR, bar_resfull, n0 + pc * 32, m0);
+          ++rit;
         }
       }
     }
@@ -489,12 +512,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // residual rows are fetched one piece ahead (the first one before the accumulator is even ready)
         uint4 res_next[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         const bf16* res_row = nullptr;
-        if (EPI == EPI_BIAS_RESIDUAL && row < p.M) {
+        if (EPI == EPI_BIAS_RESIDUAL && !RES_TMA && row < p.M) {
           res_row = p.residual + static_cast<size_t>(row) * p.ldr + n0 + part * WCOLS;
 #pragma unroll
           for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row)[i];
         }
-        if (EPI == EPI_BIAS_RESIDUAL) {
+        if (EPI == EPI_BIAS_RESIDUAL && !RES_TMA) {
           // The residual stream was last touched several kernels ago: its rows come from HBM (~1.5 us under load), which
           // a one-piece-ahead register prefetch cannot cover. Pull this thread's slice of the NEXT tile into L2 now, a whole
           // tile ahead of its use.
@@ -513,6 +536,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_rnempty[as]);
         }
+        if (RES_TMA) mbar_wait_parked(bar_resfull, it & 1);  // landed long ago: issued a main loop ahead
         mbar_wait_parked(&bar_tfull[as], aphase);
         tcgen05_fence_after();
         float2 st_carry = make_float2(0.f, 0.f);
@@ -522,11 +546,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t acc[32];
           tmem_ld_32x32(taddr + pc * 32, acc);
           uint4 res_cur[4];
+          if (RES_TMA) {
+            // piece = 128 rows x 64 B, 64B-swizzled like the output slabs: conflict-free row-per-lane reads
+            const uint8_t* rp = sRes + (col_in_tile >> 5) * (GEMM_BM * 64) + row_in_tile * 64;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
-          if (EPI == EPI_BIAS_RESIDUAL && res_row != nullptr && pc + 1 < PIECES) {
+            for (int i = 0; i < 4; ++i) res_cur[i] = *reinterpret_cast<const uint4*>(rp + ((i ^ ((row_in_tile >> 1) & 3)) << 4));
+            if (pc + 1 == PIECES) {  // this warp is done with the residual tile
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_resempty);
+            }
+          } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row + (pc + 1) * 32)[i];
+            for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
+            if (EPI == EPI_BIAS_RESIDUAL && res_row != nullptr && pc + 1 < PIECES) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) res_next[i] = reinterpret_cast<const uint4*>(res_row + (pc + 1) * 32)[i];
+            }
           }
           tmem_ld_wait();
           if (pc + 1 == PIECES) {  // every tcgen05.ld of this warp for this tile has completed: release the accumulator
@@ -600,7 +635,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int EPI, typename OutT, bool LNIN, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, gemm_res_tma(BN, EPI, CG)>;
+  CUtensorMap tmR = tmC;  // unused unless the configuration stages its residual through TMA
+  if (gemm_res_tma(BN, EPI, CG)) {
+    const int rc = make_tmap_2d_bf16(&tmR, p.residual, p.N, p.M, p.ldr, 32, GEMM_BM, /*swizzle_bytes=*/64);
+    if (rc != LRCE_OK) return rc;
+  }
   auto kern = gemm_tc_kernel<BN, EPI, OutT, LNIN, CG>;
   static thread_local uint64_t configured = 0;  // one bit per device: function attributes are per device
   if (needs_device_setup(&configured)) {
@@ -615,7 +655,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int units = sm_count() / CG;
   if (n_tiles < units) units = n_tiles;
   if (CG == 1) {
-    kern<<<units, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    kern<<<units, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(units * CG);
@@ -629,7 +669,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p);
     if (e != cudaSuccess) {
       set_error("cudaLaunchKernelEx(gemm_tc_kernel, cluster of %d): %s", CG, cudaGetErrorString(e));
       return LRCE_ECUDA;

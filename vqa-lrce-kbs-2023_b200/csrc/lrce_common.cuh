@@ -125,6 +125,34 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- cheap issue path for kernels whose MMAs are small (a few tens of tensor cycles each): with the plain helpers above,
+// issued from inside `if (lane == 0)`, every MMA costs ~60 cycles of descriptor arithmetic and R2UR waterfall loops on the
+// issuing thread (measured, tools/probes/walk_probe.cu); kept warp-uniform with one elected lane it costs ~3 instructions.
+// One lane of the (converged) warp; the MMA warp keeps its control flow warp-uniform and only the tcgen05 instructions sit
+// behind this predicate, so descriptor arithmetic stays on the uniform datapath instead of a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// K-major SWIZZLE_128B operand descriptor = {lo, hi}: hi is constant (SBO 1024 B, version 1, layout 2), lo = (address >> 4)
+// | LBO 1; operands that differ only in their start address differ only in lo, by (byte offset >> 4).
+constexpr uint32_t UMMA_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | 0x10000u; }
+template <bool ACC>
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %4};\n"
+      "mov.b64 db, {%2, %4};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(UMMA_DESC_HI_SW128), "n"(ACC ? 1 : 0)
+      : "memory");
+}
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i <- lane base+i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
   asm volatile(

@@ -1,0 +1,516 @@
+// mlp_fused.cu — the Swin MLP block (video_swin_ori.py:40-57 Mlp, :284-285 / :304 norm2 + residual) of the stage-1 blocks
+// (C = 128) as ONE kernel:   out = x + fc2( gelu( fc1( LayerNorm(x) ) ) )
+// The hidden activations (M x 512 bf16 = 925 MB per block at batch 32) never leave the SM: as two GEMMs the pair moved
+// 2.5 GB per block through HBM and ran at 78 % of the HBM roofline; fused it moves x in and out once (0.46 GB).
+//
+// One persistent CTA per SM walks 128-row tiles; the hidden dimension is processed in eight 64-wide chunks:
+//   warp 0      TMA producer : x tiles (2 k-blocks of 128 x 64, 128B swizzle, double-buffered); allocates TMEM (512 columns:
+//                              acc1 x 4, acc2 x 2). The weights travel in two 3-slot rings of 16 KB chunks (W1_j: 64 hidden
+//                              rows x 128; W2_j: 128 output rows x 64 hidden columns), each filled by the issuer that drains it
+//   warp 1      fc1 issuer   : acc1[g % 4] = x . W1_j^T   (M 128, N 64, K 128), up to four chunks ahead of fc2
+//   warp 2      fc2 issuer   : acc2[tile & 1] += H_j . W2_j^T  (M 128, N 128, K 64) — one issuer warp per product, so that the
+//                              barrier waits of one never delay the MMAs of the other on the shared tensor pipe
+//   warp 3      row statistics of the folded LayerNorm (as in gemm_tc.cu: W1 holds W diag(gamma), the rows are raw)
+//   warps 4-19  epilogue     : chunk: tcgen05.ld -> rstd (acc - mean colsum) + b' -> GELU -> bf16 A-operand tile H (128B
+//                              swizzle) in shared memory; tile end: acc2 + b2 + residual -> (mean, M2) partials -> bf16.
+//                              The residual is read from the x tile in shared memory and the result is written back IN
+//                              PLACE, so the x buffer doubles as the staging area of two 128 x 64 TMA stores.
+// What bounds it: 256 KB of weights are re-streamed from L2 for every 128-row tile (1.8 GB per block against the ~12 TB/s
+// the L2 can supply), next to 4096 tensor cycles and ~4096 MUFU cycles (GELU) per tile.
+#include <stdio.h>
+
+#include "host_common.h"
+#include "lrce_common.cuh"
+
+// MF_VARIANT != 0: remove-one-cost experiments for tools/ (timing only, results are wrong); the library is built with 0
+#ifndef MF_VARIANT
+#define MF_VARIANT 0
+#endif
+
+namespace lrce {
+
+#if MF_VARIANT == 9  // stall accounting of CTA 0 (printed at kernel end)
+#define MF_TWAIT(acc, bar, par)          \
+  do {                                   \
+    const long long t0_ = clock64();     \
+    mbar_wait_parked(bar, par);          \
+    acc += clock64() - t0_;              \
+  } while (0)
+#else
+#define MF_TWAIT(acc, bar, par) mbar_wait_parked(bar, par)
+#endif
+
+constexpr int MF_C = 128, MF_HID = 4 * MF_C, MF_HC = 64, MF_NCH = MF_HID / MF_HC;
+constexpr int MF_BM = 128;
+constexpr int MF_THREADS = 640;  // warps 0-3: producer, fc1 issuer, fc2 issuer, row statistics; warps 4-19: epilogue
+constexpr int MF_EPI_WARPS = 16;
+constexpr int MF_X_BYTES = MF_BM * MF_C * 2;   // 32 KB: two k-blocks of 128 rows x 128 B
+constexpr int MF_W_BYTES = MF_HC * MF_C * 2;   // 16 KB: W1 chunk [64 x 128] = W2 chunk [128 x 64]
+constexpr int MF_WSLOTS = 3;  // slots of EACH weight ring (W1 chunks, W2 chunks)
+constexpr int MF_H_BYTES = MF_BM * MF_HC * 2;  // 16 KB
+constexpr int MF_NB = 4;  // acc1 / H buffers: how far the fc1 issuer may run ahead of the fc2 issuer
+constexpr int MF_OFF_X = 0, MF_OFF_W = 2 * MF_X_BYTES, MF_OFF_H = MF_OFF_W + 2 * MF_WSLOTS * MF_W_BYTES;
+constexpr int MF_OFF_RN = MF_OFF_H + MF_NB * MF_H_BYTES, MF_OFF_BAR = MF_OFF_RN + 2 * MF_BM * 8;
+constexpr int MF_SMEM = MF_OFF_BAR + 512;
+constexpr int MF_TM_A1 = 0, MF_TM_A2 = MF_NB * MF_HC, MF_TM_COLS = 512;  // acc1 x 4 (64 columns each), acc2 x 2 (128 each)
+static_assert(MF_SMEM <= 232448, "fused MLP shared-memory budget");
+
+struct MlpParams {
+  int M;
+  const float *b1, *colsum1, *in_stats, *b2;
+  float in_eps;
+  float* out_stats;  // nullptr or float2 [M][4]: (mean, M2) of every 32-column chunk of the output rows
+};
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// erf-GELU as 0.5 x (1 + tanh(u)), u = x (a + b x^2 + c x^4): same fit as gemm_tc.cu (one MUFU per value)
+__device__ __forceinline__ float2 mf_gelu2(float2 x) {
+  float2 x2 = fmul2(x, x);
+  x2.x = fminf(x2.x, 64.0f);
+  x2.y = fminf(x2.y, 64.0f);
+  float2 p = ffma2(x2, make_float2(-0.00035151677f, -0.00035151677f), make_float2(0.03700564325f, 0.03700564325f));
+  p = ffma2(p, x2, make_float2(0.79750783595f, 0.79750783595f));
+  const float2 u = fmul2(p, x);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, t, hx);
+}
+
+// (mean, M2) of 32 values (four independent packed accumulators, as in gemm_tc.cu)
+__device__ __forceinline__ float2 mf_stats32(const float (&v)[32]) {
+  float2 s0 = make_float2(v[0], v[1]), s1 = make_float2(v[2], v[3]), s2 = make_float2(v[4], v[5]), s3 = make_float2(v[6], v[7]);
+#pragma unroll
+  for (int i = 8; i < 32; i += 8) {
+    s0 = fadd2(s0, make_float2(v[i + 0], v[i + 1]));
+    s1 = fadd2(s1, make_float2(v[i + 2], v[i + 3]));
+    s2 = fadd2(s2, make_float2(v[i + 4], v[i + 5]));
+    s3 = fadd2(s3, make_float2(v[i + 6], v[i + 7]));
+  }
+  s0 = fadd2(fadd2(s0, s1), fadd2(s2, s3));
+  const float mean = (s0.x + s0.y) * (1.0f / 32);
+  const float2 nm = make_float2(-mean, -mean);
+  float2 m0 = make_float2(0.f, 0.f), m1 = m0, m2 = m0, m3 = m0;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const float2 d0 = fadd2(make_float2(v[i + 0], v[i + 1]), nm), d1 = fadd2(make_float2(v[i + 2], v[i + 3]), nm);
+    const float2 d2 = fadd2(make_float2(v[i + 4], v[i + 5]), nm), d3 = fadd2(make_float2(v[i + 6], v[i + 7]), nm);
+    m0 = ffma2(d0, d0, m0);
+    m1 = ffma2(d1, d1, m1);
+    m2 = ffma2(d2, d2, m2);
+    m3 = ffma2(d3, d3, m3);
+  }
+  m0 = fadd2(fadd2(m0, m1), fadd2(m2, m3));
+  return make_float2(mean, m0.x + m0.y);
+}
+
+__global__ void __launch_bounds__(MF_THREADS, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const MlpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sX = smem + MF_OFF_X;
+  uint8_t* sW = smem + MF_OFF_W;
+  uint8_t* sH = smem + MF_OFF_H;
+  float2* s_rn = reinterpret_cast<float2*>(smem + MF_OFF_RN);
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + MF_OFF_BAR);  // [2]
+  uint64_t* x_empty = x_full + 2;                                     // [2]
+  uint64_t* w_full = x_empty + 2;                                     // [2 rings][3]: W1 chunks, W2 chunks
+  uint64_t* w_empty = w_full + 2 * MF_WSLOTS;                         // [2][3]
+  uint64_t* a1_full = w_empty + 2 * MF_WSLOTS;                        // [4]
+  uint64_t* a1_empty = a1_full + MF_NB;                               // [4]
+  uint64_t* h_full = a1_empty + MF_NB;                                // [4]
+  uint64_t* h_empty = h_full + MF_NB;                                 // [4]
+  uint64_t* a2_full = h_empty + MF_NB;                                // [2]
+  uint64_t* a2_empty = a2_full + 2;                                   // [2]
+  uint64_t* rn_full = a2_empty + 2;                                   // [2]
+  uint64_t* rn_empty = rn_full + 2;                                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rn_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.M + MF_BM - 1) / MF_BM;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1 && lane == 0) tma_prefetch_desc(&tmW1);
+  if (warp == 2 && lane == 0) tma_prefetch_desc(&tmW2);
+  if (warp == 1 && lane == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&x_full[b], 1);
+      mbar_init(&x_empty[b], 1);
+      mbar_init(&a2_full[b], 1);
+      mbar_init(&a2_empty[b], MF_EPI_WARPS);
+      mbar_init(&rn_full[b], 1);
+      mbar_init(&rn_empty[b], MF_EPI_WARPS);
+    }
+    for (int b = 0; b < MF_NB; ++b) {
+      mbar_init(&a1_full[b], 1);
+      mbar_init(&a1_empty[b], MF_EPI_WARPS);
+      mbar_init(&h_full[b], MF_EPI_WARPS);
+      mbar_init(&h_empty[b], 1);
+    }
+    for (int s = 0; s < 2 * MF_WSLOTS; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, MF_TM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      // x tiles only: each MMA issuer streams its own weight chunks (a shared producer would stall one ring on the other)
+      const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles ? (n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1, t = blockIdx.x + it * gridDim.x;
+        mbar_wait_parked(&x_empty[b], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&x_full[b], MF_X_BYTES);
+        tma_load_2d(sX + b * MF_X_BYTES, &tmX, &x_full[b], 0, t * MF_BM);
+        tma_load_2d(sX + b * MF_X_BYTES + MF_BM * 128, &tmX, &x_full[b], 64, t * MF_BM);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ fc1 issuer (warp converged, one elected lane issues)
+    // These MMAs are small (32 / 64 tensor cycles each): the issue path must cost a few instructions per MMA (warp-uniform
+    // control flow, descriptors advanced as 32-bit words: lrce_common.cuh umma_lo), and fc1 / fc2 have an issuer warp each so
+    // that one product's barrier waits never delay the other's MMAs. acc1[b] = x . W1_j^T, up to MF_NB chunks ahead of fc2.
+    constexpr uint32_t idesc1 = umma_idesc_bf16(MF_BM, MF_HC);
+    const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles ? (n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    const uint32_t x_lo = desc_lo(smem_u32(sX)), w_lo = desc_lo(smem_u32(sW));
+    int ws = 0;
+    uint32_t wph = 0, b = 0, use = 0;
+    long long tx = 0, tw = 0, ta = 0;
+    const long long tstart = clock64();
+    // this warp streams its own W1 chunks, MF_WSLOTS - 1 chunks ahead of the one it multiplies (the slot being refilled was
+    // released by the commit of the previous iteration's MMAs)
+    const int n_chunks = my_tiles * MF_NCH;
+    int ls = 0, lj = 0, lg = 0;  // slot / chunk-in-tile / running index of the next chunk to request
+    uint32_t lph = 0;
+    auto request = [&]() {
+      if (lg < n_chunks) {
+        mbar_wait_parked(&w_empty[ls], lph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&w_full[ls], MF_W_BYTES);
+          uint8_t* dst = sW + ls * MF_W_BYTES;  // hidden rows [64 j, 64 j + 64) x K = 128 as two 64 x 64 k-blocks
+          tma_load_2d(dst, &tmW1, &w_full[ls], 0, lj * MF_HC);
+          tma_load_2d(dst + MF_HC * 128, &tmW1, &w_full[ls], 64, lj * MF_HC);
+        }
+        __syncwarp();
+        ++lg;
+        if (++ls == MF_WSLOTS) { ls = 0; lph ^= 1; }
+        if (++lj == MF_NCH) lj = 0;
+      }
+    };
+    for (int i = 0; i < MF_WSLOTS - 1; ++i) request();
+#pragma unroll 1
+    for (int it = 0; it < my_tiles; ++it) {
+      MF_TWAIT(tx, &x_full[it & 1], (it >> 1) & 1);
+      const uint32_t xa = x_lo + (it & 1) * (MF_X_BYTES >> 4);
+#pragma unroll 1
+      for (int j = 0; j < MF_NCH; ++j) {
+        request();
+        MF_TWAIT(tw, &w_full[ws], wph);
+        MF_TWAIT(ta, &a1_empty[b], (use & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t wa = w_lo + ws * (MF_W_BYTES >> 4), tm_d = tmem_base + MF_TM_A1 + b * MF_HC;
+        if (elect_one()) {
+          umma_lo<false>(tm_d, xa, wa, idesc1);
+#pragma unroll
+          for (int m = 1; m < 8; ++m)  // m = 4 kb + ks
+            umma_lo<true>(tm_d, xa + (((m >> 2) * (MF_BM * 128) + (m & 3) * 32) >> 4), wa + (((m >> 2) * (MF_HC * 128) + (m & 3) * 32) >> 4),
+                          idesc1);
+          umma_commit(&w_empty[ws]);
+          umma_commit(&a1_full[b]);
+        }
+        __syncwarp();
+        if (++ws == MF_WSLOTS) { ws = 0; wph ^= 1; }
+        if (++b == MF_NB) { b = 0; ++use; }
+      }
+    }
+#if MF_VARIANT == 9
+    if (blockIdx.x == 0 && lane == 0)
+      printf("fc1 issuer: %d tiles, %lld cycles per tile; waiting per tile: x %lld, W1 %lld, acc1 free %lld\n", my_tiles,
+             (clock64() - tstart) / my_tiles, tx / my_tiles, tw / my_tiles, ta / my_tiles);
+#endif
+    (void)tx; (void)tw; (void)ta; (void)tstart;
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ fc2 issuer: acc2[tile & 1] (+)= H_j . W2_j^T
+    constexpr uint32_t idesc2 = umma_idesc_bf16(MF_BM, MF_C);
+    const int my_tiles = static_cast<int>(blockIdx.x) < n_tiles ? (n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    const uint32_t h_lo = desc_lo(smem_u32(sH)), w_lo = desc_lo(smem_u32(sW + MF_WSLOTS * MF_W_BYTES));
+    uint64_t* w2_full = w_full + MF_WSLOTS;
+    uint64_t* w2_empty = w_empty + MF_WSLOTS;
+    int ws = 0;
+    uint32_t wph = 0, b = 0, use = 0;
+    long long t2 = 0, tw = 0, th = 0;
+    const int n_chunks = my_tiles * MF_NCH;
+    int ls = 0, lj = 0, lg = 0;  // this warp streams its own W2 chunks (see the fc1 issuer)
+    uint32_t lph = 0;
+    auto request = [&]() {
+      if (lg < n_chunks) {
+        mbar_wait_parked(&w2_empty[ls], lph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&w2_full[ls], MF_W_BYTES);  // all 128 output rows x hidden columns [64 j, 64 j + 64)
+          tma_load_2d(sW + (MF_WSLOTS + ls) * MF_W_BYTES, &tmW2, &w2_full[ls], lj * MF_HC, 0);
+        }
+        __syncwarp();
+        ++lg;
+        if (++ls == MF_WSLOTS) { ls = 0; lph ^= 1; }
+        if (++lj == MF_NCH) lj = 0;
+      }
+    };
+    for (int i = 0; i < MF_WSLOTS - 1; ++i) request();
+#pragma unroll 1
+    for (int it = 0; it < my_tiles; ++it) {
+      MF_TWAIT(t2, &a2_empty[it & 1], ((it >> 1) & 1) ^ 1);  // the tile before last has left this accumulator
+      const uint32_t tm_d = tmem_base + MF_TM_A2 + (it & 1) * MF_C;
+#pragma unroll 1
+      for (int j = 0; j < MF_NCH; ++j) {
+        request();
+        MF_TWAIT(tw, &w2_full[ws], wph);
+        MF_TWAIT(th, &h_full[b], use & 1);
+        tcgen05_fence_after();
+        const uint32_t ha = h_lo + b * (MF_H_BYTES >> 4), wa = w_lo + ws * (MF_W_BYTES >> 4);
+        if (elect_one()) {
+          if (j == 0) umma_lo<false>(tm_d, ha, wa, idesc2);
+          else umma_lo<true>(tm_d, ha, wa, idesc2);
+#pragma unroll
+          for (int ks = 1; ks < 4; ++ks) umma_lo<true>(tm_d, ha + ((ks * 32) >> 4), wa + ((ks * 32) >> 4), idesc2);
+          umma_commit(&w2_empty[ws]);
+          umma_commit(&h_empty[b]);
+          if (j == MF_NCH - 1) umma_commit(&a2_full[it & 1]);
+        }
+        __syncwarp();
+        if (++ws == MF_WSLOTS) { ws = 0; wph ^= 1; }
+        if (++b == MF_NB) { b = 0; ++use; }
+      }
+    }
+#if MF_VARIANT == 9
+    if (blockIdx.x == 0 && lane == 0)
+      printf("fc2 issuer: waiting per tile: acc2 free %lld, W2 %lld, H %lld\n", t2 / my_tiles, tw / my_tiles, th / my_tiles);
+#endif
+    (void)t2; (void)tw; (void)th;
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ row statistics of the folded LayerNorm
+    // (mean, M2) partials of the four 32-column chunks of every row (emitted by the producing GEMM) -> (rstd, -rstd mean)
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      float2 part[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = min(t * MF_BM + lane + 32 * i, p.M - 1);
+        const float4* st = reinterpret_cast<const float4*>(p.in_stats) + static_cast<size_t>(row) * 2;
+        const float4 a = __ldg(st), b = __ldg(st + 1);
+        part[i][0] = make_float2(a.x, a.y); part[i][1] = make_float2(a.z, a.w);
+        part[i][2] = make_float2(b.x, b.y); part[i][3] = make_float2(b.z, b.w);
+      }
+      mbar_wait_parked(&rn_empty[it & 1], ((it >> 1) & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mean = 0.25f * (part[i][0].x + part[i][1].x + part[i][2].x + part[i][3].x);
+        float m2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float d = part[i][c].x - mean;
+          m2 += fmaf(32.0f * d, d, part[i][c].y);
+        }
+        const float rstd = rsqrtf(m2 * (1.0f / MF_C) + p.in_eps);
+        s_rn[(it & 1) * MF_BM + lane + 32 * i] = make_float2(rstd, -rstd * mean);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rn_full[it & 1]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;            // TMEM lane quarter
+    const int part = (warp - 4) >> 2;  // column group: 16 of a chunk's 64 hidden features, 32 of the 128 outputs
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int sw = row_in_tile & 7;  // 128B swizzle phase of this thread's row
+    uint32_t g = 0;
+    int it = 0;
+    long long e_a1 = 0, e_h = 0, e_a2 = 0, e_bar = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int xb = it & 1;
+      const int row = t * MF_BM + row_in_tile;
+      mbar_wait_parked(&rn_full[it & 1], (it >> 1) & 1);
+      const float2 rn = s_rn[(it & 1) * MF_BM + row_in_tile];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rn_empty[it & 1]);
+      const float2 rx = make_float2(rn.x, rn.x), ry = make_float2(rn.y, rn.y);
+      for (int j = 0; j < MF_NCH; ++j, ++g) {
+        const uint32_t b = g % MF_NB, use = g / MF_NB;
+        // fold constants of this thread's 16 hidden features (L1-resident after the first tile)
+        const int n0 = j * MF_HC + part * 16;
+        float4 cs[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          cs[i] = __ldg(reinterpret_cast<const float4*>(p.colsum1 + n0) + i);
+          bb[i] = __ldg(reinterpret_cast<const float4*>(p.b1 + n0) + i);
+        }
+        MF_TWAIT(e_a1, &a1_full[b], use & 1);
+        tcgen05_fence_after();
+        uint32_t acc[16];
+        tmem_ld_32x16(t_lane + MF_TM_A1 + b * MF_HC + part * 16, acc);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a1_empty[b]);
+        uint32_t h[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // LayerNorm folded into fc1: rstd (acc - mean colsum) + b'  ==  rstd acc + (-rstd mean) colsum + b'
+          const float2 lo = ffma2(rx, make_float2(__uint_as_float(acc[4 * i + 0]), __uint_as_float(acc[4 * i + 1])),
+                                  ffma2(ry, make_float2(cs[i].x, cs[i].y), make_float2(bb[i].x, bb[i].y)));
+          const float2 hi = ffma2(rx, make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])),
+                                  ffma2(ry, make_float2(cs[i].z, cs[i].w), make_float2(bb[i].z, bb[i].w)));
+#if MF_VARIANT == 1  // no GELU
+          const float2 gl = lo, gh = hi;
+#else
+          const float2 gl = mf_gelu2(lo), gh = mf_gelu2(hi);
+#endif
+          h[2 * i] = pack_bf16x2(gl.x, gl.y);
+          h[2 * i + 1] = pack_bf16x2(gh.x, gh.y);
+        }
+        MF_TWAIT(e_h, &h_empty[b], (use & 1) ^ 1);  // fc2 of chunk g-4 has consumed this H buffer
+        uint8_t* hrow = sH + b * MF_H_BYTES + row_in_tile * 128;
+#if MF_VARIANT != 2  // 2: no H stores, no proxy fence
+        *reinterpret_cast<uint4*>(hrow + (((2 * part) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(hrow + (((2 * part + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+        fence_proxy_async_smem();
+#else
+        if (h[0] == 0x12345678u && h[5] == 0x9abcdef0u) *reinterpret_cast<uint4*>(hrow) = make_uint4(h[0], h[1], h[2], h[3]);
+#endif
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[b]);
+      }
+      // ---- tile end: out = acc2 + b2 + x, in place in the x tile (this thread: row, columns [32 part, 32 part + 32))
+      MF_TWAIT(e_a2, &a2_full[it & 1], (it >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t acc[32];
+      tmem_ld_32x32(t_lane + MF_TM_A2 + (it & 1) * MF_C + part * 32, acc);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a2_empty[it & 1]);
+      uint8_t* xrow = sX + xb * MF_X_BYTES + (part >> 1) * (MF_BM * 128) + row_in_tile * 128;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 r = *reinterpret_cast<const uint4*>(xrow + ((((part & 1) * 4 + i) ^ sw) << 4));
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b2 + part * 32 + 8 * i));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b2 + part * 32 + 8 * i + 4));
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 res = bf16x2_to_f32x2(rw[k]);
+          v[8 * i + 2 * k] = __uint_as_float(acc[8 * i + 2 * k]) + bv[2 * k] + res.x;
+          v[8 * i + 2 * k + 1] = __uint_as_float(acc[8 * i + 2 * k + 1]) + bv[2 * k + 1] + res.y;
+        }
+      }
+      if (p.out_stats != nullptr && row < p.M)
+        reinterpret_cast<float2*>(p.out_stats)[static_cast<size_t>(row) * (MF_C / 32) + part] = mf_stats32(v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(xrow + ((((part & 1) * 4 + i) ^ sw) << 4)) = o;
+      }
+      fence_proxy_async_smem();
+#if MF_VARIANT == 9
+      const long long tb0 = clock64();
+#endif
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // every epilogue warp has written its part of the tile
+#if MF_VARIANT == 9
+      e_bar += clock64() - tb0;
+#endif
+      if (warp == 4 && lane == 0) {
+        const uint32_t src = smem_u32(sX + xb * MF_X_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmO)),
+                       "r"(src + kb * (MF_BM * 128)), "r"(kb * 64), "r"(t * MF_BM)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the x buffer may be refilled
+        mbar_arrive(&x_empty[xb]);
+      }
+    }
+    if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#if MF_VARIANT == 9
+    if (blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 19))
+      printf("epilogue warp %d: waiting per tile: acc1 ready %lld, H free %lld, acc2 ready %lld, tile barrier %lld\n", warp, e_a1 / it,
+             e_h / it, e_a2 / it, e_bar / it);
+#endif
+    (void)e_a1; (void)e_h; (void)e_a2; (void)e_bar;
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, MF_TM_COLS);
+  }
+}
+
+}  // namespace lrce
+
+using namespace lrce;
+
+extern "C" int lrce_mlp_fused_bf16(const void* x, int ldx, const void* w1, const float* b1, const float* colsum1,
+                                   const float* in_stats, float in_eps, const void* w2, const float* b2, void* out, int ldo,
+                                   float* out_stats, int M, int C, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(x && w1 && b1 && colsum1 && in_stats && w2 && b2 && out, "lrce_mlp_fused_bf16: null operand");
+  LRCE_REQUIRE(C == MF_C, "lrce_mlp_fused_bf16 is specialised for C = %d (the stage-1 blocks); got C = %d", MF_C, C);
+  LRCE_REQUIRE(M > 0 && ldx % 8 == 0 && ldo % 8 == 0, "lrce_mlp_fused_bf16: bad shape / pitch (M=%d ldx=%d ldo=%d)", M, ldx, ldo);
+  LRCE_REQUIRE(((reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(colsum1) | reinterpret_cast<uintptr_t>(b2) |
+                 reinterpret_cast<uintptr_t>(in_stats)) & 15) == 0 &&
+                   (out_stats == nullptr || (reinterpret_cast<uintptr_t>(out_stats) & 7) == 0),
+               "lrce_mlp_fused_bf16: parameter vectors must be 16-byte aligned");
+  static thread_local uint64_t configured = 0;  // one bit per device
+  if (needs_device_setup(&configured)) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(mlp_fused_kernel, smem=%d): %s", MF_SMEM, cudaGetErrorString(e));
+      return LRCE_ECUDA;
+    }
+    mark_device_setup(&configured);
+  }
+  CUtensorMap tmX, tmW1, tmW2, tmO;
+  rc = make_tmap_2d_bf16(&tmX, x, MF_C, M, ldx, 64, MF_BM);
+  if (rc == LRCE_OK) rc = make_tmap_2d_bf16(&tmW1, w1, MF_C, MF_HID, MF_C, 64, MF_HC);
+  if (rc == LRCE_OK) rc = make_tmap_2d_bf16(&tmW2, w2, MF_HID, MF_C, MF_HID, 64, MF_C);
+  if (rc == LRCE_OK) rc = make_tmap_2d_bf16(&tmO, out, MF_C, M, ldo, 64, MF_BM);
+  if (rc != LRCE_OK) return rc;
+  MlpParams p;
+  p.M = M;
+  p.b1 = b1; p.colsum1 = colsum1; p.in_stats = in_stats; p.b2 = b2;
+  p.in_eps = in_eps;
+  p.out_stats = out_stats;
+  const int n_tiles = (M + MF_BM - 1) / MF_BM;
+  int grid = sm_count();
+  if (grid > n_tiles) grid = n_tiles;
+  mlp_fused_kernel<<<grid, MF_THREADS, MF_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW1, tmW2, tmO, p);
+  return check_launch("mlp_fused_kernel");
+}

@@ -18,6 +18,7 @@ SWIN_CKPT = "./pretrained_models/swin_base_patch244_window877_kinetics600_22k.pt
 # Segments per L2-resident slab for stages 1..4 (0 = whole batch); LRCE_B200_SLABS="a,b,c,d" overrides. Measured on B200 at
 # batch 32 (profiles/README.md): 0,0,0,0 -> 19.8 ms; 12,48,0,0 -> 19.6 ms; 6,24,0,0 -> 20.2 ms; 4,16,0,0 -> 20.9 ms — the HBM
 # traffic saved is paid back in per-launch fill/drain, so whole-batch execution stays the default.
+FUSED_MLP = os.environ.get("LRCE_B200_FUSED_MLP", "1") != "0"  # A/B switch for tools/ (the product default is fused)
 SLAB_SEGMENTS = tuple(int(v) for v in os.environ.get("LRCE_B200_SLABS", "0,0,0,0").split(","))
 
 
@@ -253,9 +254,12 @@ class SwinTransformer3D(_PackedModule):
                     del qkv
                     ops.gemm(att, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_b)
                     del att
-                    hid = ops.gemm(x, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU, ln_in=(st_b, b["c1"], 1e-5))
-                    ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_a)
-                    del hid
+                    if C == 128 and FUSED_MLP:  # stage 1: fc1 -> GELU -> fc2 per 128-row tile, hidden never in HBM
+                        ops.mlp_fused(x, b["w1"], b["b1"], b["c1"], st_b, 1e-5, b["w2"], b["b2"], out=x, stats_out=st_a)
+                    else:
+                        hid = ops.gemm(x, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU, ln_in=(st_b, b["c1"], 1e-5))
+                        ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_a)
+                        del hid
                     if taps is not None and j < 2 and i < 3:
                         taps[f"stage{i}.block{j}"] = x.view(n, D, H, W, C).clone()
                 if not last:

@@ -110,9 +110,11 @@ int lrce_window_bias_pack(const float* table, void* bias_dense, int n_heads, voi
 int lrce_window_attention_bf16(const void* qkv, void* out, const void* bias_dense, int n_seg, int D, int H, int W, int C,
                                int n_heads, int shift_h, int shift_w, void* stream);
 
-/* profiling hook: per-warp mbarrier-wait cycle counters of CTA 0 of later lrce_window_attention_bf16 launches are
- * accumulated into buf (device, 224 int64, zeroed by the caller; layout in csrc/window_attn.cu); NULL switches it off. */
-int lrce_debug_attention_timing(long long* buf);
+/* Instrumented instantiation of the same kernel for tools/ (no library-side state: the buffer is a per-call argument):
+ * per-warp mbarrier-wait cycle counters of CTA 0 are accumulated into prof (device, 224 int64, zeroed by the caller; layout
+ * in csrc/window_attn.cu); a wait longer than ~50 ms is reported there instead of hanging (watchdog). */
+int lrce_window_attention_profile(const void* qkv, void* out, const void* bias_dense, int n_seg, int D, int H, int W, int C,
+                                  int n_heads, int shift_h, int shift_w, void* stream, long long* prof);
 
 /* ---- recurrent cross-modal encoder ------------------------------------------------------------------------------ */
 

@@ -33,17 +33,15 @@ for name, hw, C, heads in stages:
         byts = qkv.numel() * 2 + out.numel() * 2
         print(f"{name} shift={shift} {ms*1e3:8.1f} us  items={items} core {flops/ms/1e9:6.1f} TFLOP/s  {byts/ms/1e6:7.1f} GB/s  {ms*1e6/items*296:.0f} ns/item/CTA", flush=True)
 
-# ---- where the warps of CTA 0 wait (profiling hook), stage 3 shifted
+# ---- where the warps of CTA 0 wait (instrumented instantiation), stage 3 shifted
 from lrce_b200 import _lib
 hw, C, heads = 14, 512, 16
 T = 3 * hw * hw
 qkv = torch.randn(n_seg * T, 3 * C, device="cuda").bfloat16()
 bias = ops.window_bias_pack(torch.randn(2535, heads, device="cuda") * 0.5)
 buf = torch.zeros(224, dtype=torch.int64, device="cuda")
-_lib.lib().lrce_debug_attention_timing(buf.data_ptr())
-ops.window_attention(qkv, bias, n_seg, 3, hw, hw, C, heads, (3, 3))
+ops.window_attention(qkv, bias, n_seg, 3, hw, hw, C, heads, (3, 3), prof=buf)
 torch.cuda.synchronize()
-_lib.lib().lrce_debug_attention_timing(0)
 t = buf.cpu().tolist()
 n, total = t[192], t[193]
 print(f"CTA 0: {n} items, {total} cycles = {total / max(n, 1):.0f} cycles/item")

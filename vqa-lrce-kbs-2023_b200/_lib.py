@@ -31,7 +31,7 @@ _SIGNATURES = {
     "lrce_text_posembed_ln": [_vp, _i] + [_vp] * 4 + [_f, _vp, _i, _i, _vp],
     "lrce_encoder_walk_pack_bytes": [_i, _i],
     "lrce_encoder_walk_pack": [_vp, _i, _vp, _vp, _i, _vp, _vp],
-    "lrce_debug_attention_timing": [_vp],
+    "lrce_window_attention_profile": [_vp, _vp, _vp] + [_i] * 8 + [_vp, _vp],
     "lrce_encoder_walk": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lrce_encoder_walk_profile": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i],
     "lrce_add_ln_768": [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _i, _f, _i, _u64, _vp, _vp],

@@ -195,8 +195,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t x_lo = desc_lo(smem_u32(sX)), w_lo = desc_lo(smem_u32(sW));
     int ws = 0;
     uint32_t wph = 0, b = 0, use = 0;
-    long long tx = 0, tw = 0, ta = 0;
-    const long long tstart = clock64();
+    [[maybe_unused]] long long tx = 0, tw = 0, ta = 0;
+    [[maybe_unused]] const long long tstart = MF_VARIANT == 9 ? clock64() : 0;
     // this warp streams its own W1 chunks, MF_WSLOTS - 1 chunks ahead of the one it multiplies (the slot being refilled was
     // released by the commit of the previous iteration's MMAs)
     const int n_chunks = my_tiles * MF_NCH;
@@ -248,7 +248,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       printf("fc1 issuer: %d tiles, %lld cycles per tile; waiting per tile: x %lld, W1 %lld, acc1 free %lld\n", my_tiles,
              (clock64() - tstart) / my_tiles, tx / my_tiles, tw / my_tiles, ta / my_tiles);
 #endif
-    (void)tx; (void)tw; (void)ta; (void)tstart;
   } else if (warp == 2) {
     // ------------------------------------------------------------------ fc2 issuer: acc2[tile & 1] (+)= H_j . W2_j^T
     constexpr uint32_t idesc2 = umma_idesc_bf16(MF_BM, MF_C);
@@ -258,7 +257,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint64_t* w2_empty = w_empty + MF_WSLOTS;
     int ws = 0;
     uint32_t wph = 0, b = 0, use = 0;
-    long long t2 = 0, tw = 0, th = 0;
+    [[maybe_unused]] long long t2 = 0, tw = 0, th = 0;
     const int n_chunks = my_tiles * MF_NCH;
     int ls = 0, lj = 0, lg = 0;  // this warp streams its own W2 chunks (see the fc1 issuer)
     uint32_t lph = 0;
@@ -305,7 +304,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (blockIdx.x == 0 && lane == 0)
       printf("fc2 issuer: waiting per tile: acc2 free %lld, W2 %lld, H %lld\n", t2 / my_tiles, tw / my_tiles, th / my_tiles);
 #endif
-    (void)t2; (void)tw; (void)th;
   } else if (warp == 3) {
     // ------------------------------------------------------------------ row statistics of the folded LayerNorm
     // (mean, M2) partials of the four 32-column chunks of every row (emitted by the producing GEMM) -> (rstd, -rstd mean)
@@ -345,7 +343,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int sw = row_in_tile & 7;  // 128B swizzle phase of this thread's row
     uint32_t g = 0;
     int it = 0;
-    long long e_a1 = 0, e_h = 0, e_a2 = 0, e_bar = 0;
+    [[maybe_unused]] long long e_a1 = 0, e_h = 0, e_a2 = 0, e_bar = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int xb = it & 1;
       const int row = t * MF_BM + row_in_tile;
@@ -461,7 +459,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       printf("epilogue warp %d: waiting per tile: acc1 ready %lld, H free %lld, acc2 ready %lld, tile barrier %lld\n", warp, e_a1 / it,
              e_h / it, e_a2 / it, e_bar / it);
 #endif
-    (void)e_a1; (void)e_h; (void)e_a2; (void)e_bar;
   }
 
   tcgen05_fence_before();

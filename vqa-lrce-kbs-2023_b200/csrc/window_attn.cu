@@ -146,7 +146,7 @@ struct WaShared {
   uint64_t *qk_full, *qk_empty, *v_full, *v_empty;  // [2] each: staging buffers
   uint64_t *s_full, *s_free;                        // [2]: per row tile
   uint64_t *p_full, *o_full;                        // [4]: [row tile][buffer]
-  long long* prof;  // profiling hook (lrce_debug_attention_timing): [24 warps][8] cycle counters of CTA 0, or nullptr
+  long long* prof;  // lrce_window_attention_profile: [24 warps][8] cycle counters of CTA 0, or nullptr
 };
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -609,17 +609,11 @@ __global__ void build_dense_bias_kernel(const float* __restrict__ table, bf16* _
 
 using namespace lrce;
 
-static long long* g_attn_prof = nullptr;
-// Profiling hook, not part of the product path: when buf (device, 224 zeroed int64) is non-NULL, CTA 0 of the following
-// lrce_window_attention_bf16 launches accumulates, per warp w at buf[8 w ..], the cycles spent in each kind of mbarrier wait
+// Instrumented instantiation (lrce_window_attention_profile, tools only; a per-call argument, the library keeps no profiling
+// state): CTA 0 accumulates into buf (device, 224 zeroed int64), per warp w at buf[8 w ..], the cycles spent in each kind of mbarrier wait
 // (softmax warps: [0] S ready, [1] P v done, [4] TMEM load, [5] maximum, [6] probabilities, [7] epilogue; loader: [0] q/k
 // buffer free, [3] v buffer free; MMA: [0] S released, [1] q/k landed, [2] P ready, [3] v landed), plus buf[192] units and
 // buf[193] total cycles of CTA 0; buf[196 + w] != 0 reports a watchdog hit of warp w.
-extern "C" int lrce_debug_attention_timing(long long* buf) {
-  g_attn_prof = buf;
-  return LRCE_OK;
-}
-
 static int geom_3x7x7(StageGeom* g, int D, int H, int W, int sh, int sw) {
   LRCE_REQUIRE(D == 3 && H % 7 == 0 && W % 7 == 0 && H > 0 && W > 0,
                "window attention is specialised for the clamped (3,7,7) window of LRCE's 5-frame segments; got grid "
@@ -666,8 +660,8 @@ static int get_maps(const WaMaps** out, const void* qkv, int n_seg, int H, int W
   return LRCE_OK;
 }
 
-extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void* bias_dense, int n_seg, int D, int H,
-                                          int W, int C, int n_heads, int shift_h, int shift_w, void* stream) {
+static int window_attention_launch(const void* qkv, void* out, const void* bias_dense, int n_seg, int D, int H, int W, int C,
+                                   int n_heads, int shift_h, int shift_w, void* stream, long long* prof) {
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   StageGeom g;
@@ -693,15 +687,26 @@ extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void
   int grid = sm_count();  // one persistent CTA per SM (it owns all 512 TMEM columns)
   if (grid > n_units) grid = static_cast<int>(n_units);
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
-  if (g_attn_prof != nullptr)  // profiling hook armed: instrumented instantiation
+  if (prof != nullptr)  // instrumented instantiation
     window_attention_kernel<true><<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
         *maps, reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e,
-        g_attn_prof);
+        prof);
   else
     window_attention_kernel<false><<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
         *maps, reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e,
         nullptr);
   return check_launch("window_attention_kernel");
+}
+
+extern "C" int lrce_window_attention_bf16(const void* qkv, void* out, const void* bias_dense, int n_seg, int D, int H,
+                                          int W, int C, int n_heads, int shift_h, int shift_w, void* stream) {
+  return window_attention_launch(qkv, out, bias_dense, n_seg, D, H, W, C, n_heads, shift_h, shift_w, stream, nullptr);
+}
+
+extern "C" int lrce_window_attention_profile(const void* qkv, void* out, const void* bias_dense, int n_seg, int D, int H,
+                                             int W, int C, int n_heads, int shift_h, int shift_w, void* stream, long long* prof) {
+  LRCE_REQUIRE(prof != nullptr, "lrce_window_attention_profile: prof buffer required");
+  return window_attention_launch(qkv, out, bias_dense, n_seg, D, H, W, C, n_heads, shift_h, shift_w, stream, prof);
 }
 
 extern "C" int lrce_window_bias_pack(const float* table, void* bias_dense, int n_heads, void* stream) {

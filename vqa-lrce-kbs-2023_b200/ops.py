@@ -188,12 +188,18 @@ def window_bias_pack(table):
     return out
 
 
-def window_attention(qkv, bias_dense, n_seg, D, H, W, C, n_heads, shift_hw, out=None):
-    """qkv bf16 [n_seg*D*H*W, 3C] (natural order) -> bf16 [n_seg*D*H*W, C] (natural order)."""
+def window_attention(qkv, bias_dense, n_seg, D, H, W, C, n_heads, shift_hw, out=None, prof=None):
+    """qkv bf16 [n_seg*D*H*W, 3C] (natural order) -> bf16 [n_seg*D*H*W, C] (natural order). `prof` (tools only): int64 [224]
+    device buffer -> the instrumented instantiation (lrce_window_attention_profile)."""
     _req(qkv, torch.bfloat16, "qkv"); _req(bias_dense, torch.bfloat16, "bias_dense")
     assert qkv.is_contiguous() and qkv.shape == (n_seg * D * H * W, 3 * C)
     if out is None:
         out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.bfloat16)
+    if prof is not None:
+        assert prof.dtype == torch.int64 and prof.is_cuda and prof.numel() >= 224
+        _call("lrce_window_attention_profile", _ptr(qkv), _ptr(out), _ptr(bias_dense), n_seg, D, H, W, C, n_heads,
+              shift_hw[0], shift_hw[1], _stream(), _ptr(prof))
+        return out
     _call("lrce_window_attention_bf16", _ptr(qkv), _ptr(out), _ptr(bias_dense), n_seg, D, H, W, C, n_heads,
           shift_hw[0], shift_hw[1], _stream(),
           # core FLOPs as SURVEY.md 8(d) counts them: QK^T + PV = 4 * 147^2 * 32 per (window, head)

@@ -166,6 +166,11 @@ int lrce_encoder_walk_pack(const void* layer_table, int n_layers, const float* f
 int lrce_encoder_walk(const void* packed, int n_layers, const void* kv_video, const void* kv_text, int ld_kv, const float* tok0,
                       const float* f_gamma, const float* f_beta, float eps, int n_out, int act, float* out, float* tokens_tap,
                       int rows, int S, int Tv, int Lt, int n_cand, void* stream);
+/* The host-side plan lrce_encoder_walk derives for `rows` rows when `max_clusters` 16-CTA clusters can be resident (7 on a
+ * B200 at this kernel's shared-memory footprint): rows per cluster (<= 8), row groups, clusters launched, ring slots, dynamic
+ * shared memory. Pure host arithmetic, no CUDA call. */
+int lrce_encoder_walk_plan(int rows, int max_clusters, int* rows_per_cluster, int* n_groups, int* clusters, int* ring_slots,
+                           int* smem_bytes);
 /* Instrumented instantiation of the same kernel for tools/ (no library-side state: everything is a per-call argument):
  * prof = device int64 [CTAs][32] receiving the cycles thread 0 of each CTA spent per sub-step of the dependency chain;
  * max_clusters > 0 caps the number of clusters; variant = 1 runs the production code, other values select code variants kept

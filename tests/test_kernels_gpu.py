@@ -368,3 +368,25 @@ def test_encoder_walk_pack_layout(ops, n_out):
         assert torch.allclose(params[n], want, rtol=1e-5, atol=2e-4), (n, (params[n] - want).abs().max().item())
     assert torch.equal(tail[0], layers[-1]["n3g"]) and torch.equal(tail[1], layers[-1]["n3b"])
     assert torch.equal(hbias[:n_out], fc_b) and not hbias[n_out:].any()
+
+
+@pytest.mark.parametrize("kind,B", [("oe", 60), ("mc", 13), ("oe", 1)])
+def test_encoder_walk_row_grouping_invariance(kind, B):
+    """Rows walk independently: a batch that needs several row groups per cluster (and several passes) must give, bit for
+    bit, what the same rows give in small batches of one group each (fusionv3.py:41-51 has no cross-row term)."""
+    import lrce_b200
+
+    torch.manual_seed(5)
+    if kind == "mc":
+        m = lrce_b200.LRCEMultipleChoice(768, 1, 0.1, [7, 7], 1024, 5, [3], 40).cuda().eval()
+        tf = torch.randn(B, 5, 40, 768, device="cuda")
+    else:
+        m = lrce_b200.LRCEOpenEnded(768, 1000, 0.1, [7, 7], 1024, 5, [3], 32).cuda().eval()
+        tf = torch.randn(B, 32, 768, device="cuda")
+    vf = torch.randn(B, 3, 3, 49, 1024, device="cuda").bfloat16()
+    step = 1 if kind == "mc" else 6
+    with torch.no_grad():
+        y_all = m(vf, tf)
+        y_parts = torch.cat([m(vf[i:i + step], tf[i:i + step]) for i in range(0, B, step)])
+    assert torch.isfinite(y_all).all()
+    assert torch.equal(y_all, y_parts), (y_all - y_parts).abs().max().item()

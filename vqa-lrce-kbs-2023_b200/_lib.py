@@ -33,6 +33,7 @@ _SIGNATURES = {
     "lrce_encoder_walk_pack": [_vp, _i, _vp, _vp, _i, _vp, _vp],
     "lrce_window_attention_profile": [_vp, _vp, _vp] + [_i] * 8 + [_vp, _vp],
     "lrce_encoder_walk": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "lrce_encoder_walk_plan": [_i, _i, _vp, _vp, _vp, _vp, _vp],
     "lrce_encoder_walk_profile": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i],
     "lrce_add_ln_768": [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _i, _f, _i, _u64, _vp, _vp],
     "lrce_ln_bwd_768": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _ll, _f, _i, _f, _i, _u64, _vp, _vp],

@@ -1073,6 +1073,27 @@ static int walk_max_clusters(int* out) {
   return LRCE_OK;
 }
 
+// Host-side plan of a walk over `rows` rows on a device that can keep `max_clusters` 16-CTA clusters resident: rows per
+// cluster (spread over every cluster, at most WK_NPAD rows per pass), row groups, clusters launched, ring slots that fit next
+// to the per-row buffers, dynamic shared memory. Pure host arithmetic (no CUDA call): also what tests/ checks on the CPU.
+extern "C" int lrce_encoder_walk_plan(int rows, int max_clusters, int* rows_per_cluster, int* n_groups, int* clusters,
+                                      int* ring_slots, int* smem_bytes) {
+  LRCE_REQUIRE(rows > 0 && max_clusters > 0 && rows_per_cluster && n_groups && clusters && ring_slots && smem_bytes,
+               "lrce_encoder_walk_plan: bad arguments (rows=%d, max_clusters=%d)", rows, max_clusters);
+  const int passes = (rows + WK_NPAD * max_clusters - 1) / (WK_NPAD * max_clusters);
+  const int rpc = (rows + passes * max_clusters - 1) / (passes * max_clusters);
+  const int groups = (rows + rpc - 1) / rpc;
+  int ns = WK_MAX_SLOTS;
+  while (ns > 0 && walk_smem(rpc, ns).total > WK_SMEM_MAX) --ns;
+  LRCE_REQUIRE(ns >= 3, "lrce_encoder_walk: shared memory leaves only %d ring slots for %d rows per cluster", ns, rpc);
+  *rows_per_cluster = rpc;
+  *n_groups = groups;
+  *clusters = groups < max_clusters ? groups : max_clusters;
+  *ring_slots = ns;
+  *smem_bytes = walk_smem(rpc, ns).total;
+  return LRCE_OK;
+}
+
 static int walk_launch(const void* packed, int n_layers, const void* kv_video, const void* kv_text, int ld_kv, const float* tok0,
                        const float* f_gamma, const float* f_beta, float eps, int n_out, int act, float* out, float* tokens_tap,
                        int rows, int S, int Tv, int Lt, int n_cand, void* stream, long long* prof, int max_clusters, int variant) {
@@ -1094,14 +1115,9 @@ static int walk_launch(const void* packed, int n_layers, const void* kv_video, c
   rc = walk_max_clusters(&ncl);
   if (rc != LRCE_OK) return rc;
   if (max_clusters > 0 && max_clusters < ncl) ncl = max_clusters;
-  // rows per cluster: spread the rows over every cluster that can be resident, at most WK_NPAD rows per pass
-  const int passes = (rows + WK_NPAD * ncl - 1) / (WK_NPAD * ncl);
-  const int rpc = (rows + passes * ncl - 1) / (passes * ncl);
-  const int n_groups = (rows + rpc - 1) / rpc;
-  const int clusters = n_groups < ncl ? n_groups : ncl;
-  int ns = WK_MAX_SLOTS;
-  while (ns > 0 && walk_smem(rpc, ns).total > WK_SMEM_MAX) --ns;
-  LRCE_REQUIRE(ns >= 3, "lrce_encoder_walk: shared memory leaves only %d ring slots", ns);
+  int rpc = 0, n_groups = 0, clusters = 0, ns = 0, smem_bytes = 0;
+  rc = lrce_encoder_walk_plan(rows, ncl, &rpc, &n_groups, &clusters, &ns, &smem_bytes);
+  if (rc != LRCE_OK) return rc;
   const WalkPackLayout lay = walk_pack_layout(n_layers, n_out);
   const uint8_t* base = reinterpret_cast<const uint8_t*>(packed);
   WalkParams p;
@@ -1132,7 +1148,7 @@ static int walk_launch(const void* packed, int n_layers, const void* kv_video, c
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * WK_CL);
   cfg.blockDim = dim3(WK_THREADS);
-  cfg.dynamicSmemBytes = static_cast<size_t>(walk_smem(rpc, ns).total);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

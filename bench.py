@@ -41,9 +41,10 @@ GFLOP_PER_CLIP = 303.96  # Swin-B 3 x 96.354 + canonical encode
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
-GEMM_DRAM_BYTES_PER_STEP = 17607.3e6 + 12948.1e6  # gemm_tc_kernel family, one batch-32 forward (ncu launch list)
-GEMM_LAUNCHES_NCU = 103.0
-GEMM_TRAFFIC_SOURCE = "profiles/r01_launches_v3_summary.md"
+# gemm_tc_kernel launches of Swin + encoder in one batch-32 forward (ncu launch list; BERT's 48 launches excluded: 304 MB)
+GEMM_DRAM_BYTES_PER_STEP = (14844.4e6 - 303.7e6) + 10667.5e6
+GEMM_LAUNCHES_NCU = 99.0
+GEMM_TRAFFIC_SOURCE = "profiles/r02_launches_v1_summary.md"
 
 
 def load_peaks():

@@ -142,12 +142,12 @@ class LRCEOpenEnded(_PackedModule):
             kv_w.append(ca_w[d:])
             kv_b.append(ca_b[d:])
         pk["kv_w"], pk["kv_b"] = bf(torch.cat(kv_w)), f32(torch.cat(kv_b))  # [12*1536, 768]: layer-major, [k | v]
-        # device table of per-layer pointers in the order lrce_encoder_walk_pack documents (include/lrce_b200.h); the fp32
-        # masters are only needed until the pack kernels have run
+        # device table of per-layer pointers in the order lrce_encoder_walk_pack documents (include/lrce_b200.h). The fp32
+        # masters are only needed by the pack kernels, which are enqueued on the current stream: the caching allocator hands
+        # their blocks out again only to work ordered after those kernels on the same stream, so no synchronisation is needed.
         table = torch.tensor([[t.data_ptr() for t in row] for row in walk_rows], dtype=torch.int64, device=dev)
         pk["walk_packed"] = ops.encoder_walk_pack(table, len(walk_rows), f32(self.final_fc.weight), pk["fc_b"],
                                                   self.final_fc.out_features)
-        torch.cuda.current_stream(dev).synchronize()
         return pk
 
     def _validate(self, video_features, text_features, n_cand):

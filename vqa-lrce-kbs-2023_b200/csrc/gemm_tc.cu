@@ -357,9 +357,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread; the pair's leader)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (the pair's leader)
+    // the whole warp walks the loop and one elected lane issues: with the warp converged the descriptors stay in uniform
+    // registers and an MMA costs ~3 instructions (a lane-0 branch makes every operand a per-MMA R2UR waterfall, ~60 cycles)
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN);
+      const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -372,23 +375,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait_parked(&bar_full[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint32_t a_lo = a_lo0 + stage * (Cfg::A_BYTES >> 4), b_lo = b_lo0 + stage * (Cfg::B_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            if (CG == 2)
-              umma_bf16_ss_pair(tmem_d, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                                (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_bf16_ss(tmem_d, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_lo_acc<CG>(tmem_d, a_lo + k * 2, b_lo + k * 2, idesc, k != 0 ? 1u : static_cast<uint32_t>(kb));
+            if (CG == 2) umma_commit_pair(&bar_empty[stage]);  // frees the stage in both CTAs
+            else umma_commit(&bar_empty[stage]);
           }
-          if (CG == 2) umma_commit_pair(&bar_empty[stage]);  // frees the stage in both CTAs
-          else umma_commit(&bar_empty[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) umma_commit_pair(&bar_tfull[as]);  // each CTA's epilogue drains its own half
-        else umma_commit(&bar_tfull[as]);
+        if (elect_one()) {
+          if (CG == 2) umma_commit_pair(&bar_tfull[as]);  // each CTA's epilogue drains its own half
+          else umma_commit(&bar_tfull[as]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 3) {

@@ -153,6 +153,34 @@ __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(UMMA_DESC_HI_SW128), "n"(ACC ? 1 : 0)
       : "memory");
 }
+// the same with a run-time accumulate flag, for one CTA (CG = 1) or a CTA pair (CG = 2)
+template <int CG>
+__device__ __forceinline__ void umma_lo_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %4};\n"
+        "mov.b64 db, {%2, %4};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(UMMA_DESC_HI_SW128), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %4};\n"
+        "mov.b64 db, {%2, %4};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(UMMA_DESC_HI_SW128), "r"(accumulate)
+        : "memory");
+}
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i <- lane base+i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
   asm volatile(

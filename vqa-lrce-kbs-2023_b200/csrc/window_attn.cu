@@ -21,9 +21,10 @@
 //                           below), double-buffered, completion on mbarriers.
 //   warps 21,22  MMA      : one thread each, row tile 0 (slots 0..127) / row tile 1 (slots 128..159):
 //                           S = q k^T [M=128, N=160, K=32] (both operands K-major, 64B swizzle), then O = P v
-//                           [M=128, N=32, K=160] (v consumed MN-major exactly as TMA delivered it) and L = P 1
-//                           [M=128, N=16, K=160]: the row sums of the bf16 probabilities come from the tensor pipe,
-//                           which idles, not from the softmax warps, which are the bottleneck (measured: -6 %).
+//                           [M=128, N=48, K=160] with B = [v | 1]: v consumed MN-major exactly as TMA delivered it, plus
+//                           a second N atom of ones, so that columns 32..47 are the row sums L = P 1 of the bf16
+//                           probabilities: they come from the tensor pipe, which idles, with the A reads P v pays anyway,
+//                           not from the softmax warps, which are the bottleneck.
 //                           Accumulators in TMEM: S0, S1 (2 x 160 columns), O | L double-buffered per tile (4 x 48).
 //   warps 0-15   softmax  : row tile 0, four warps per TMEM lane quarter (thread = row, warp = 40 key columns).
 //   warps 16-19  softmax  : row tile 1. Its 32 slots are loaded FOUR times into the q tile, so every TMEM lane quarter of
@@ -64,17 +65,17 @@ constexpr int WA_P0_BYTES = 128 * WA_KEYS * 2;                        // 40960: 
 constexpr int WA_P1_BYTES = 32 * WA_KEYS * 2;  // 10240: P of row tile 1 (the MMA's rows 32..127 alias what follows: unused lanes)
 constexpr int WA_BIAS_ROWS = 155;                                    // last valid slot + 1
 constexpr int WA_BIAS_HEAD_BYTES = WA_KEYS * WA_BIAS_PITCH * 2;      // 51200 per head in global memory
-constexpr int WA_BIAS_COPY_BYTES = (WA_BIAS_ROWS + 2) * WA_BIAS_PITCH * 2;  // rows 0..154 + float bmax[160] (rows 155,156)
+constexpr int WA_BIAS_COPY_BYTES = (WA_BIAS_ROWS + 1) * WA_BIAS_PITCH * 2;  // rows 0..154 + bf16 bmax[160] (row 155)
 constexpr int WA_OFF_STAGE = 0;
 constexpr int WA_OFF_P0 = 2 * WA_STAGE_BYTES;
 constexpr int WA_OFF_P1 = WA_OFF_P0 + 2 * WA_P0_BYTES;
 constexpr int WA_OFF_BIAS = WA_OFF_P1 + 2 * WA_P1_BYTES;
 constexpr int WA_OFF_BMAX = WA_OFF_BIAS + WA_BIAS_ROWS * WA_BIAS_PITCH * 2;
 constexpr int WA_OFF_BAR = WA_OFF_BIAS + WA_BIAS_COPY_BYTES;   // mbarriers, TMEM slot, watchdog flag: 192 B
-constexpr int WA_OFF_ONES = WA_OFF_BAR + 192;  // 16 x 16 bf16 ones (B operand of L = P 1), 512 B
+constexpr int WA_OFF_ONES = WA_OFF_BAR + 192;  // 16 keys x 64 B of bf16 ones: the second N atom of the P v operand (row sums L = P 1)
 constexpr int WA_OFF_M = WA_OFF_BIAS + WA_BIAS_HEAD_BYTES;     // float [2][4][128] + [2][4][32]: partial raw-score maxima
 constexpr int WA_SMEM = WA_OFF_M + (2 * 4 * 128 + 2 * 4 * 32) * 4;
-static_assert(WA_OFF_ONES + 512 <= WA_OFF_M && WA_OFF_ONES % 16 == 0, "barrier block and ones tile must fit behind the bias rows");
+static_assert(WA_OFF_ONES + 1024 <= WA_OFF_M && WA_OFF_ONES % 64 == 0, "barrier block and ones tile must fit behind the bias rows");
 static_assert(WA_SMEM <= 227 * 1024, "window attention shared-memory budget");
 static_assert(WA_OFF_P1 + WA_P1_BYTES + 128 * WA_KEYS * 2 <= WA_SMEM, "row tile 1's A operand must stay inside shared memory");
 
@@ -109,6 +110,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(512 >> 4) << 32;   // sbo: 8 rows x 64 B
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;          // layout type 4 = SWIZZLE_64B
+  return d;
+}
+
+// MN-major 64B-swizzle operand wider than one 32-element atom: atom a of the N direction starts lbo_bytes * a behind the first
+__device__ __forceinline__ uint64_t umma_desc_sw64_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
   return d;
 }
 
@@ -230,7 +242,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
   // 4-way bank conflict
   const bf16* bias_row = reinterpret_cast<const bf16*>(smem + WA_OFF_BIAS) + brow * WA_BIAS_PITCH;
   const int bias_sw = (brow >> 1) & 3;
-  const float* bmax = reinterpret_cast<const float*>(smem + WA_OFF_BMAX) + brow;
+  const bf16* bmax = reinterpret_cast<const bf16*>(smem + WA_OFF_BMAX) + brow;
   // shift mask (video_swin_ori.py:346-358) of a bottom / right border window: key group k of this warp is masked for this
   // row iff they lie on different sides of the h seam (bit k of mh) or of the w seam (bit k of mw)
   const int row_cls = (slot >= 48) + (slot >= 88) + (slot >= 128);
@@ -340,7 +352,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
     for (int k = 0; k < 4; ++k) mx = fmaxf(mx, sMax[((j & 1) * 4 + k) * mrows + prow]);
-    const float nbound = -fmaf(mx, cx.scale_log2e, *bmax);  // -(upper bound of every t_ij of the row)
+    const float nbound = -fmaf(mx, cx.scale_log2e, __bfloat162float(*bmax));  // -(upper bound of every t_ij of the row)
     if (timing) { const long long tc = clock64(); sh.prof[warp * 8 + 5] += tc - tc0; tc0 = tc; }  // [5] maximum + exchange
     // ---- p = exp2(s * scale*log2e + bias + mask - bound) -> bf16 A-operand tile (buffer j & 1: P v(j-2) has completed,
     // observed at the epilogue of unit j-2); pad columns carry a bias of -inf
@@ -416,7 +428,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
 
   // ---- one-time setup: zero the staging and P buffers (pad slots stay zero forever), barriers, TMEM
   for (int i = tid; i < WA_OFF_BIAS / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < 32) reinterpret_cast<uint4*>(smem + WA_OFF_ONES)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  if (tid < 64) reinterpret_cast<uint4*>(smem + WA_OFF_ONES)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (warp == WA_WARP_MMA0 && lane == 0) {
     *reinterpret_cast<volatile int*>(smem + WA_OFF_BAR + 184) = 0;  // watchdog abort flag (profiling hook only)
     for (int b = 0; b < 2; ++b) {
@@ -508,10 +520,12 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
     }
   } else if (warp == WA_WARP_MMA0 || warp == WA_WARP_MMA1) {
     // ===================================================================== MMA issuers: warp 21 -> row tile 0, 22 -> tile 1
-    if (lane == 0 && n_my > 0) {
+    // the whole warp walks the loop and one elected lane issues: with the warp converged the descriptors live in uniform registers
+    // and an MMA costs a few instructions (behind a lane-0 branch every operand is a per-MMA R2UR waterfall, ~60 cycles x 22 / unit)
+    if (n_my > 0) {
       const int tile = warp == WA_WARP_MMA1;
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_KEYS);          // A, B K-major
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);  // B (= v) MN-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, WA_ON) | (1u << 16);  // B (= [v | 1]) MN-major
       uint64_t* s_full = sh.s_full + tile;
       uint64_t* s_free = sh.s_free + tile;
       uint64_t* p_full = sh.p_full + 2 * tile;
@@ -523,10 +537,13 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
       auto issue_s = [&](int j) {
         const uint32_t b = smem0 + WA_OFF_STAGE + (j & 1) * WA_STAGE_BYTES;
         const uint64_t dq = umma_desc_sw64(b + tile * (128 * 64)), dk = umma_desc_sw64(b + WA_Q_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) umma_bf16_ss(tm_s, dq + ((kk * 32) >> 4), dk + ((kk * 32) >> 4), idesc_s, kk);
-        umma_commit(s_full);
-        umma_commit(&sh.qk_empty[j & 1]);
+          for (int kk = 0; kk < 2; ++kk) umma_bf16_ss(tm_s, dq + ((kk * 32) >> 4), dk + ((kk * 32) >> 4), idesc_s, kk);
+          umma_commit(s_full);
+          umma_commit(&sh.qk_empty[j & 1]);
+        }
+        __syncwarp();
       };
       timed_wait<PROF>(sh, &sh.qk_full[0], 0, 1, 0);
       tcgen05_fence_after();
@@ -541,18 +558,23 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
         timed_wait<PROF>(sh, p_full + (j & 1), (j >> 1) & 1, 2, j);  // P(j) in smem, output buffer j & 1 drained (unit j-2)
         timed_wait<PROF>(sh, &sh.v_full[j & 1], (j >> 1) & 1, 3, j);
         tcgen05_fence_after();
-        const uint64_t dv = umma_desc_sw64(smem0 + WA_OFF_STAGE + (j & 1) * WA_STAGE_BYTES + WA_Q_BYTES + WA_K_BYTES);
+        // B = [v | 1]: N = 48 = the 32 dims of v (one 64-byte swizzle atom per key) + a second atom of ones (columns 32..47 = the row
+        // sums L = P 1 of the bf16 probabilities, for free with the same A reads). The ones are ONE 16-key slab: every K step
+        // moves the start address 1024 B ahead and the atom stride (lbo) 1024 B back, so the second atom never moves.
+        const uint32_t v_addr = smem0 + WA_OFF_STAGE + (j & 1) * WA_STAGE_BYTES + WA_Q_BYTES + WA_K_BYTES;
+        const uint64_t dv = umma_desc_sw64_lbo(v_addr, smem0 + WA_OFF_ONES - v_addr);
         const uint64_t dp = umma_desc_nosw(smem0 + (tile ? WA_OFF_P1 + (j & 1) * WA_P1_BYTES : WA_OFF_P0 + (j & 1) * WA_P0_BYTES),
                                            128, (WA_KEYS / 8) * 128);
         const uint32_t tm_oj = tm_o + (j & 1) * WA_ON;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < WA_KEYS / 16; ++kk)  // 16 keys per step: 2 cores of P (256 B), 2 row groups of v (1024 B)
-          umma_bf16_ss(tm_oj, dp + ((kk * 256) >> 4), dv + ((kk * 1024) >> 4), idesc_o, kk);
-        umma_commit(&sh.v_empty[j & 1]);
-#pragma unroll
-        for (int kk = 0; kk < WA_KEYS / 16; ++kk)  // L = P 1: row sums of the bf16 probabilities, columns 32..47 of the buffer
-          umma_bf16_ss(tm_oj + 32, dp + ((kk * 256) >> 4), umma_desc_nosw(smem0 + WA_OFF_ONES, 128, 256), umma_idesc_bf16(128, 16), kk);
-        umma_commit(o_full + (j & 1));
+          for (int kk = 0; kk < WA_KEYS / 16; ++kk)  // 16 keys per step: 2 cores of P (256 B), 2 row groups of v (1024 B)
+            umma_bf16_ss(tm_oj, dp + ((kk * 256) >> 4), dv + ((kk * 1024) >> 4) - (static_cast<uint64_t>((kk * 1024) >> 4) << 16), idesc_o,
+                         kk);
+          umma_commit(&sh.v_empty[j & 1]);
+          umma_commit(o_full + (j & 1));
+        }
+        __syncwarp();
       }
     }
   } else if (warp < 20) {
@@ -578,14 +600,14 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
 
 // dense[h][slot_i][slot_j] = table[rel_index(tok_i, tok_j)][h] * log2(e) for rows 0..154 (pad key columns -inf, pad rows 0),
 // the 16-byte chunks of row i stored at chunk index (j / 8) ^ ((i >> 1) & 3) (bank-conflict-free row-per-lane reads);
-// rows 155, 156 of every head hold float bmax[160] = max_j dense[h][slot_i][.] (0 for pad rows)
+// row 155 of every head holds bf16 bmax[160] = max_j dense[h][slot_i][.] (0 for pad rows; exact: a maximum of bf16 values)
 __global__ void build_dense_bias_kernel(const float* __restrict__ table, bf16* __restrict__ dense, StageGeom g,
                                         int n_heads) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_heads * WA_KEYS) return;
   const int si = idx % WA_KEYS, h = idx / WA_KEYS;
   bf16* head = dense + static_cast<size_t>(h) * WA_KEYS * WA_BIAS_PITCH;
-  float* bmax = reinterpret_cast<float*>(head + WA_BIAS_ROWS * WA_BIAS_PITCH);
+  bf16* bmax = head + WA_BIAS_ROWS * WA_BIAS_PITCH;
   const int ti = slot_token_377(si);
   float mx = -INFINITY;
   for (int sj = 0; sj < WA_KEYS; ++sj) {
@@ -602,7 +624,7 @@ __global__ void build_dense_bias_kernel(const float* __restrict__ table, bf16* _
     }
     if (si < WA_BIAS_ROWS) head[si * WA_BIAS_PITCH + (((sj >> 3) ^ ((si >> 1) & 3)) << 3) + (sj & 7)] = v;
   }
-  bmax[si] = mx;
+  bmax[si] = __float2bfloat16(mx);
 }
 
 }  // namespace lrce

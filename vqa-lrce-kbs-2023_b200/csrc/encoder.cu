@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) video_posembed_ln_kernel(const bf16* __re
                                                                 const float* __restrict__ emb_clip, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float eps, bf16* __restrict__ out,
                                                                 int B, int S, int T, int P) {
+  griddep_wait();  // programmatic dependent launch (host_common.h): no global access before this point
+  griddep_launch();
   const int lane = threadIdx.x & 31;
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long rows = static_cast<long long>(B) * S * T * (P + 1);
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) text_posembed_ln_kernel(const TextT* __re
                                                                const float* __restrict__ emb_pos, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, bf16* __restrict__ out,
                                                                int Bt, int L) {
+  griddep_wait();
+  griddep_launch();
   const int lane = threadIdx.x & 31;
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= static_cast<long long>(Bt) * (L + 1)) return;
@@ -67,9 +71,13 @@ extern "C" int lrce_video_posembed_ln(const void* proj, const float* emb_cls, co
   LRCE_REQUIRE(proj && emb_cls && emb_pos && emb_len && emb_clip && gamma && beta && out && B > 0 && S > 0 && T > 0 && P > 0,
                "lrce_video_posembed_ln: bad arguments");
   const long long rows = static_cast<long long>(B) * S * T * (P + 1);
-  video_posembed_ln_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(proj), emb_cls, emb_pos, emb_len, emb_clip, gamma, beta, eps,
-      reinterpret_cast<bf16*>(out), B, S, T, P);
+  cudaError_t e = launch_pdl(video_posembed_ln_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(proj), emb_cls, emb_pos, emb_len,
+                             emb_clip, gamma, beta, eps, reinterpret_cast<bf16*>(out), B, S, T, P);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(video_posembed_ln_kernel): %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
   return check_launch("video_posembed_ln_kernel");
 }
 
@@ -81,12 +89,17 @@ extern "C" int lrce_text_posembed_ln(const void* text, int text_fp32, const floa
   const long long rows = static_cast<long long>(Bt) * (L + 1);
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e;
   if (text_fp32)
-    text_posembed_ln_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(text), emb_cls, emb_pos, gamma, beta,
-                                                          eps, reinterpret_cast<bf16*>(out), Bt, L);
+    e = launch_pdl(text_posembed_ln_kernel<float>, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const float*>(text), emb_cls, emb_pos,
+                   gamma, beta, eps, reinterpret_cast<bf16*>(out), Bt, L);
   else
-    text_posembed_ln_kernel<bf16><<<blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(text), emb_cls, emb_pos, gamma, beta,
-                                                         eps, reinterpret_cast<bf16*>(out), Bt, L);
+    e = launch_pdl(text_posembed_ln_kernel<bf16>, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const bf16*>(text), emb_cls, emb_pos,
+                   gamma, beta, eps, reinterpret_cast<bf16*>(out), Bt, L);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(text_posembed_ln_kernel): %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
   return check_launch("text_posembed_ln_kernel");
 }
 

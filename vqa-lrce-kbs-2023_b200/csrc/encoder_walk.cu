@@ -228,6 +228,8 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   cluster_sync_all();  // every CTA's barriers exist before the first remote copy can target them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // programmatic dependent launch: the set-up above overlaps the previous kernel's tail, global memory only below
+  griddep_launch();
 
   const int n_keys = p.Tv + p.Lt;
   // (row, head) attention units in head-major order u = head * rpc + row: unit u's output is the 128-byte row at byte
@@ -1150,13 +1152,13 @@ static int walk_launch(const void* packed, int n_layers, const void* kv_video, c
   cfg.blockDim = dim3(WK_THREADS);
   cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = WK_CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1 + pdl_attr(attr + 1);
   cudaError_t e = prof == nullptr ? (variant == 0 ? cudaLaunchKernelEx(&cfg, encoder_walk_kernel<false, 0>, tmW, tmV, tmT, p)
                                                   : cudaLaunchKernelEx(&cfg, encoder_walk_kernel<false, 1>, tmW, tmV, tmT, p))
                   : variant == 0  ? cudaLaunchKernelEx(&cfg, encoder_walk_kernel<true, 0>, tmW, tmV, tmT, p)

@@ -322,6 +322,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlaps the tail of the previous kernel of the stream (programmatic dependent launch); global memory is
+  // touched only below. The next kernel may be scheduled as soon as every CTA got here (it holds its TMEM by then).
+  griddep_wait();
+  griddep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -657,20 +661,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int units = sm_count() / CG;
   if (n_tiles < units) units = n_tiles;
   if (CG == 1) {
-    kern<<<units, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
+    cudaError_t e = launch_pdl(kern, dim3(units), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, p);
+    if (e != cudaSuccess) {
+      set_error("cudaLaunchKernelEx(gemm_tc_kernel): %s", cudaGetErrorString(e));
+      return LRCE_ECUDA;
+    }
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(units * CG);
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1 + pdl_attr(attr + 1);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p);
     if (e != cudaSuccess) {
       set_error("cudaLaunchKernelEx(gemm_tc_kernel, cluster of %d): %s", CG, cudaGetErrorString(e));

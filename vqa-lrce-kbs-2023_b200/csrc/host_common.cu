@@ -1,6 +1,8 @@
 // host_common.cu — error convention, arch gate and TMA descriptor encoding for liblrce_b200.so.
 #include "host_common.h"
 
+#include <stdlib.h>
+
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -49,6 +51,14 @@ int check_launch(const char* what) {
     return LRCE_ECUDA;
   }
   return LRCE_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LRCE_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int sm_count() {

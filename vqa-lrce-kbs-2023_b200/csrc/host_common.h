@@ -34,6 +34,30 @@ int current_device();
 bool needs_device_setup(const uint64_t* mask);
 void mark_device_setup(uint64_t* mask);
 
+// Programmatic dependent launch: a kernel launched with this attribute may start (block scheduling, barrier / TMEM set-up, tensor
+// map prefetch) while the tail of the previous kernel of the stream drains, once every block of that kernel has executed
+// griddepcontrol.launch_dependents; the kernel itself must execute griddepcontrol.wait (griddep_wait() in lrce_common.cuh) before
+// its first access to global memory. LRCE_B200_PDL=0 launches without the attribute (A/B runs).
+bool pdl_enabled();
+inline int pdl_attr(cudaLaunchAttribute* a) {
+  if (!pdl_enabled()) return 0;
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  cfg.numAttrs = pdl_attr(at);
+  cfg.attrs = at;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace lrce
 
 #define LRCE_REQUIRE(cond, ...)          \

@@ -55,6 +55,12 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
       : "memory");
 }
 
+// programmatic dependent launch (host side: launch_pdl / pdl_attr in host_common.h). griddep_wait(): block until the kernels this
+// launch depends on have completed and their writes are visible — before the FIRST global-memory access of the kernel; a no-op
+// for a normal launch. griddep_launch(): this block no longer holds back the start of the next kernel of the stream.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------------

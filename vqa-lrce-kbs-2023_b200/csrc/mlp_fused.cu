@@ -171,6 +171,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // programmatic dependent launch: the set-up above overlaps the previous kernel's tail, global memory only below
+  griddep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -508,6 +510,11 @@ extern "C" int lrce_mlp_fused_bf16(const void* x, int ldx, const void* w1, const
   const int n_tiles = (M + MF_BM - 1) / MF_BM;
   int grid = sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  mlp_fused_kernel<<<grid, MF_THREADS, MF_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW1, tmW2, tmO, p);
+  cudaError_t e = launch_pdl(mlp_fused_kernel, dim3(grid), dim3(MF_THREADS), MF_SMEM, reinterpret_cast<cudaStream_t>(stream), tmX, tmW1,
+                             tmW2, tmO, p);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(mlp_fused_kernel): %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
   return check_launch("mlp_fused_kernel");
 }

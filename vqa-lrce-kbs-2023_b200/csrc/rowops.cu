@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, long long rows,
                                                              int D, int H, int W) {
+  griddep_wait();  // programmatic dependent launch (host_common.h): no global access before this point
+  griddep_launch();
   constexpr int LANES = (C / 8 < 32) ? C / 8 : 32;
   constexpr int VEC = C / (8 * LANES);
   constexpr int ROWS_PER_WARP = 32 / LANES;
@@ -106,8 +108,12 @@ static int launch_ln(const void* x, void* y, const float* g, const float* b, flo
   constexpr int ROWS_PER_WARP = 32 / LANES;
   const long long warps = (rows + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
   const long long blocks = (warps + 7) / 8;
-  layernorm_rows_kernel<C, MERGE, OutT><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-      reinterpret_cast<const bf16*>(x), reinterpret_cast<OutT*>(y), g, b, eps, rows, D, H, W);
+  cudaError_t e = launch_pdl(layernorm_rows_kernel<C, MERGE, OutT>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s,
+                             reinterpret_cast<const bf16*>(x), reinterpret_cast<OutT*>(y), g, b, eps, rows, D, H, W);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(layernorm_rows_kernel): %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
   return check_launch("layernorm_rows_kernel");
 }
 
@@ -142,6 +148,8 @@ __device__ __forceinline__ float4 load_px4(const uint8_t* p) {
 template <typename PixT>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const PixT* __restrict__ clips, bf16* __restrict__ A,
                                                            int n_seg, int T, int Hin, int Win) {
+  griddep_wait();  // the output buffer may still be read by the previous kernel of the stream
+  griddep_launch();
   const int D = (T + 1) / 2, Hp = Hin / 4, Wp = Win / 4;
   const long long total = static_cast<long long>(n_seg) * D * Hp * Wp * 6;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -256,8 +264,12 @@ static int patch_gather(const PixT* clips, void* A, int n_seg, int T, int Hin, i
   LRCE_REQUIRE(Hin % 4 == 0 && Win % 4 == 0, "%s: frame size %dx%d must be a multiple of the 4x4 patch", what, Hin, Win);
   LRCE_REQUIRE((reinterpret_cast<uintptr_t>(clips) & (4 * sizeof(PixT) - 1)) == 0, "%s: clips must be aligned to 4 pixels", what);
   const long long total = static_cast<long long>(n_seg) * ((T + 1) / 2) * (Hin / 4) * (Win / 4) * 6;
-  patch_gather_kernel<PixT><<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      clips, reinterpret_cast<bf16*>(A), n_seg, T, Hin, Win);
+  cudaError_t e = launch_pdl(patch_gather_kernel<PixT>, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), clips, reinterpret_cast<bf16*>(A), n_seg, T, Hin, Win);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(patch_gather_kernel): %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
   return check_launch("patch_gather_kernel");
 }
 

@@ -457,6 +457,10 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the set-up above (176 KB of shared-memory fills, barriers, TMEM) overlaps the tail of the previous kernel of the stream
+  // (programmatic dependent launch); global memory is touched only below
+  griddep_wait();
+  griddep_launch();
 
   if (warp == WA_WARP_LOADER) {
     // ===================================================================== loader: 15 TMA boxes per unit
@@ -709,14 +713,18 @@ static int window_attention_launch(const void* qkv, void* out, const void* bias_
   int grid = sm_count();  // one persistent CTA per SM (it owns all 512 TMEM columns)
   if (grid > n_units) grid = static_cast<int>(n_units);
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e;
   if (prof != nullptr)  // instrumented instantiation
-    window_attention_kernel<true><<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-        *maps, reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e,
-        prof);
+    e = launch_pdl(window_attention_kernel<true>, dim3(grid), dim3(WA_THREADS), WA_SMEM, s, *maps, reinterpret_cast<bf16*>(out),
+                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e, prof);
   else
-    window_attention_kernel<false><<<grid, WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-        *maps, reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e,
-        nullptr);
+    e = launch_pdl(window_attention_kernel<false>, dim3(grid), dim3(WA_THREADS), WA_SMEM, s, *maps, reinterpret_cast<bf16*>(out),
+                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e, static_cast<long long*>(nullptr));
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(window_attention_kernel): %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
   return check_launch("window_attention_kernel");
 }
 

@@ -42,9 +42,9 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 
 
 # gemm_tc_kernel launches of Swin + encoder in one batch-32 forward (ncu launch list; BERT's 48 launches excluded: 304 MB)
-GEMM_DRAM_BYTES_PER_STEP = (14844.4e6 - 303.7e6) + 10667.5e6
+GEMM_DRAM_BYTES_PER_STEP = (14850.3e6 - 303.7e6) + 10667.2e6
 GEMM_LAUNCHES_NCU = 99.0
-GEMM_TRAFFIC_SOURCE = "profiles/r02_launches_v1_summary.md"
+GEMM_TRAFFIC_SOURCE = "profiles/r02_launches_v2_summary.md"
 
 
 def load_peaks():

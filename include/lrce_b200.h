@@ -140,6 +140,18 @@ int lrce_mlp_fused_bf16(const void* x, int ldx, const void* w1, const float* b1,
                         float in_eps, const void* w2, const float* b2, void* out, int ldo, float* out_stats, int M, int C,
                         void* stream);
 
+/* The Swin MLP block of the stage-2 / stage-3 blocks (C = 256 / 512) as ONE kernel with the hidden activations kept in L2
+ * (csrc/gemm_tc.cu, mlp_l2_kernel): same contract as lrce_mlp_fused_bf16 (video_swin_ori.py:40-57, :284-285, :304), statistics
+ * in chunks of `in_chunk` = 64 columns. Every CTA pair walks its 256-row tiles through fc1 (folded LayerNorm + bias + GELU) into
+ * its private 256 x 4C bf16 slice of `scratch`, then through fc2 (K = 4C, bias + residual x + out_stats) reading that slice
+ * back; the scratch (lrce_mlp_l2_scratch_bytes(C) bytes, 16-byte aligned, contents undefined afterwards) is overwritten by
+ * every row tile and therefore stays in L2. Replaces two lrce_gemm_bf16 calls (EPI_BIAS_GELU + EPI_BIAS_RESIDUAL) and the
+ * DRAM round trip of the hidden rows between them. */
+size_t lrce_mlp_l2_scratch_bytes(int C);
+int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const float* b1, const float* colsum1, const float* in_stats,
+                     int in_chunk, float in_eps, const void* w2, const float* b2, void* out, int ldo, float* out_stats,
+                     void* scratch, size_t scratch_bytes, int M, int C, void* stream);
+
 #define LRCE_ACT_NONE 0
 #define LRCE_ACT_GELU 1
 #define LRCE_ACT_RELU 2

@@ -157,6 +157,37 @@ def test_mlp_fused_vs_two_gemms_and_torch(ops, M, inplace):
     assert ((got[..., 1] - want[..., 1]).abs() / want[..., 1].clamp_min(1e-3)).max().item() < 2e-2
 
 
+@pytest.mark.parametrize("C", [256, 512])
+@pytest.mark.parametrize("M", [256, 300, 148 * 128 * 2 + 77])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_mlp_l2_is_the_two_gemm_path(ops, C, M, inplace):
+    """lrce_mlp_l2_bf16 (video_swin_ori.py:40-57, :284-285, :304; stages 2 and 3) walks every 256-row tile through fc1 and fc2 with
+    the hidden rows in an L2-resident scratch: same operands, same k order and same epilogues as the two lrce_gemm_bf16 calls it
+    replaces, so the rows and their statistics are bit-identical to that path (and within bf16 of the fp32 formula). Run twice:
+    the scratch is reused and must not leak between launches."""
+    x = (seeded((M, C), 21, 1.5) + 0.4).bfloat16().cuda()
+    w1, b1 = seeded((4 * C, C), 22, 0.04).cuda(), seeded((4 * C,), 23, 0.3).cuda()
+    w2, b2 = seeded((C, 4 * C), 24, 0.04).cuda(), seeded((C,), 25, 0.3).cuda()
+    g, beta = (1 + 0.2 * seeded((C,), 26)).cuda(), (0.2 * seeded((C,), 27)).cuda()
+    ref = x.float() + torch.nn.functional.gelu(torch.nn.functional.layer_norm(x.float(), (C,), g, beta, 1e-5) @ w1.t() + b1) @ w2.t() + b2
+    wg = (w1.double() * g.double()[None]).bfloat16()
+    colsum = wg.double().sum(1).float()
+    bias1 = (b1.double() + w1.double() @ beta.double()).float()
+    nc = C // ops.stats_chunk(C)
+    st_in = chunk_stats(x)
+    hid = ops.gemm(x, wg, bias1, epilogue=ops.EPI_BIAS_GELU, ln_in=(st_in, colsum, 1e-5))
+    st_two = torch.zeros(M * nc * 2, device="cuda")
+    two = ops.gemm(hid, w2.bfloat16(), b2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, stats_out=st_two)
+    for _ in range(2):
+        st = torch.zeros(M * nc * 2, device="cuda")
+        xin = x.clone()
+        y = ops.mlp_l2(xin, wg, bias1, colsum, st_in, 1e-5, w2.bfloat16(), b2, out=xin if inplace else None, stats_out=st)
+        torch.cuda.synchronize()
+        assert torch.equal(y, two), rel_l2(y, two)
+        assert torch.equal(st, st_two)
+    assert rel_l2(y, ref) < 6e-3, rel_l2(y, ref)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # row kernels
 # ------------------------------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblrce_b200.so")
 
 _c = ctypes
-_vp, _i, _f, _ll, _u64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong, _c.c_ulonglong
+_vp, _i, _f, _ll, _u64, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong, _c.c_ulonglong, _c.c_size_t
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGNATURES = {
@@ -19,6 +19,8 @@ _SIGNATURES = {
     "lrce_last_error": [],
     "lrce_gemm_bf16": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp, _f, _vp, _vp],
     "lrce_mlp_fused_bf16": [_vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
+    "lrce_mlp_l2_scratch_bytes": [_i],
+    "lrce_mlp_l2_bf16": [_vp, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _i, _vp, _vp, _sz, _i, _i, _vp],
     "lrce_layernorm_bf16": [_vp, _vp, _vp, _vp, _f, _ll, _i, _i, _vp],
     "lrce_patch_merge_ln_bf16": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp],
     "lrce_patch_gather_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -50,7 +52,7 @@ _SIGNATURES = {
     "lrce_bert_embed_ln": [_vp] * 7 + [_f, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "lrce_bert_attention": [_vp, _vp, _vp, _i, _i, _i, _vp],
 }
-_RESTYPES = {"lrce_last_error": _c.c_char_p, "lrce_encoder_walk_pack_bytes": _c.c_size_t}
+_RESTYPES = {"lrce_last_error": _c.c_char_p, "lrce_encoder_walk_pack_bytes": _c.c_size_t, "lrce_mlp_l2_scratch_bytes": _c.c_size_t}
 
 _lib = None
 

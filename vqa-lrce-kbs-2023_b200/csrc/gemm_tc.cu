@@ -720,6 +720,311 @@ static int dispatch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   return LRCE_EINVAL;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Row-tile-fused MLP of a Swin block (stages 2 and 3):  out = x + W2 gelu(W1 LN(x) + b1) + b2  with the hidden rows in L2
+// ------------------------------------------------------------------------------------------------------------------------
+// fc1 and fc2 as two launches move the hidden activations (M x 4C bf16: 231 MB per stage-3 block) through HBM twice, and
+// under sustained load this kernel family runs at the board's power cap, where DRAM traffic is paid in clock. fc2 of a row
+// tile needs fc1 of the SAME rows only, so one persistent kernel walks, per CTA pair, a row tile of 256 rows through
+//   NT1 = 4C / 256 tiles of fc1 (LayerNorm fold + bias + GELU epilogue)  ->  bf16 hidden rows into the pair's private scratch
+//   NT2 =  C / 256 tiles of fc2 (K = 4C, A = the scratch rows the CTA wrote itself; bias + residual + row statistics)
+// with the same producer / issuer / epilogue pipeline as gemm_tc_kernel (CTA pairs, 256 x 256 tiles, 2 TMEM accumulators).
+// The scratch is 256 x 4C bf16 per pair (74 MB for C = 512 on 74 pairs) and is overwritten by every row tile, so it lives in
+// the 126 MB L2: the hidden activations never reach DRAM. No bubble at the fc1 -> fc2 switch: fc2's k-block kb reads hidden
+// columns [64 kb, 64 kb + 64) = fc1 tile kb / 4, and only the last four k-blocks need the tile whose epilogue is still running
+// when fc2's main loop starts (`h_ready[j]`: 16 epilogue warps -> the CTA's own producer, after cp.async.bulk.wait_group 0).
+struct MlpL2Params {
+  int M, C;
+  const float* in_stats;  // float2 [M][C / in_chunk]: (mean, M2) partials of x (the producer of x emitted them)
+  int in_chunk;
+  float in_eps;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+              const __grid_constant__ CUtensorMap tmHs, const __grid_constant__ CUtensorMap tmHl,
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO,
+              const __grid_constant__ CUtensorMap tmR, const GemmParams p1, const GemmParams p2, const MlpL2Params mp) {
+  constexpr int BN = 256, CG = 2;
+  using Cfg = GemmCfg<BN, CG, true>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int WCOLS = BN / 4, PIECES = WCOLS / 32;
+  constexpr int MAX_NT1 = 8;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* sC = sB + STAGES * Cfg::B_BYTES;
+  uint8_t* sRes = sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES;
+  float2* s_rn = reinterpret_cast<float2*>(sRes + Cfg::RES_BYTES);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sRes + Cfg::RES_BYTES + Cfg::RN_BYTES);
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_tfull = bar_empty + STAGES;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint64_t* bar_rnfull = bar_tempty + 2;
+  uint64_t* bar_rnempty = bar_rnfull + 2;
+  uint64_t* bar_resfull = bar_rnempty + 2;
+  uint64_t* bar_resempty = bar_resfull + 1;
+  uint64_t* h_ready = bar_resempty + 1;  // [MAX_NT1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + MAX_NT1);
+  static_assert((2 * STAGES + 10 + MAX_NT1) * 8 + 4 <= 256, "barrier block");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const int unit = static_cast<int>(blockIdx.x >> 1);
+  const int n_units = static_cast<int>(gridDim.x >> 1);
+  const int row_off = cta_rank * GEMM_BM;
+  const bool leader = cta_rank == 0;
+  const int n_rt = (mp.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
+  const int NT1 = 4 * mp.C / BN, NT2 = mp.C / BN;
+  const int nkb1 = mp.C / GEMM_BK, nkb2 = 4 * mp.C / GEMM_BK;
+  const int h0 = unit * (GEMM_BM * CG) + row_off;  // this CTA's rows of the scratch
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmHs);
+    tma_prefetch_desc(&tmHl);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bar_tfull[a], 1);
+      mbar_init(&bar_tempty[a], GEMM_EPI_WARPS * CG);
+      mbar_init(&bar_rnfull[a], 1);
+      mbar_init(&bar_rnempty[a], GEMM_EPI_WARPS);
+    }
+    mbar_init(bar_resfull, 1);
+    mbar_init(bar_resempty, GEMM_EPI_WARPS);
+    for (int j = 0; j < MAX_NT1; ++j) mbar_init(&h_ready[j], GEMM_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0, rit = 0, rt_it = 0;
+      uint32_t phase = 0;
+      auto load_kb = [&](const CUtensorMap* ta, int a_row, const CUtensorMap* tb, int b_row, int kb) {
+        mbar_wait_parked(&bar_empty[stage], phase ^ 1);
+        if (leader) mbar_expect_tx(&bar_full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+        tma_load_2d_pair(sA + stage * Cfg::A_BYTES, ta, &bar_full[stage], kb * GEMM_BK, a_row);
+        tma_load_2d_pair(sB + stage * Cfg::B_BYTES, tb, &bar_full[stage], kb * GEMM_BK, b_row);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int rt = unit; rt < n_rt; rt += n_units, ++rt_it) {
+        const int m0 = rt * (GEMM_BM * CG) + row_off;
+        for (int s = 0; s < NT1; ++s)
+          for (int kb = 0; kb < nkb1; ++kb) load_kb(&tmX, m0, &tmW1, s * BN + cta_rank * (BN / 2), kb);
+        for (int s = 0; s < NT2; ++s) {
+          for (int kb = 0; kb < nkb2; ++kb) {
+            if (s == 0 && (kb & 3) == 0) {
+              // hidden columns [64 kb, 64 kb + 256) = fc1 tile kb / 4 of this row tile: stored and complete?
+              mbar_wait_parked(&h_ready[kb >> 2], rt_it & 1);
+              asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            load_kb(&tmHl, h0, &tmW2, s * BN + cta_rank * (BN / 2), kb);
+          }
+          // the residual rows of this fc2 tile (= x, not yet overwritten: the tile's own epilogue does that), a main loop ahead
+          mbar_wait_parked(bar_resempty, (rit & 1) ^ 1);
+          mbar_expect_tx(bar_resfull, Cfg::RES_BYTES);
+#pragma unroll
+          for (int pc = 0; pc < BN / 32; ++pc) tma_load_2d(sRes + pc * (GEMM_BM * 64), &tmR, bar_resfull, s * BN + pc * 32, m0);
+          ++rit;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (the pair's leader; elected lane)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN);
+      const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int rt = unit; rt < n_rt; rt += n_units) {
+        for (int s = 0; s < NT1 + NT2; ++s, ++it) {
+          const int n_kb = s < NT1 ? nkb1 : nkb2;
+          const int as = it & 1;
+          mbar_wait_parked(&bar_tempty[as], ((it >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + as * BN;
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait_parked(&bar_full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t a_lo = a_lo0 + stage * (Cfg::A_BYTES >> 4), b_lo = b_lo0 + stage * (Cfg::B_BYTES >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k)
+                umma_lo_acc<CG>(tmem_d, a_lo + k * 2, b_lo + k * 2, idesc, k != 0 ? 1u : static_cast<uint32_t>(kb));
+              umma_commit_pair(&bar_empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (elect_one()) umma_commit_pair(&bar_tfull[as]);
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ row statistics of LN(x), once per row tile
+    const int n_chunks = mp.C / mp.in_chunk;
+    const float cw = static_cast<float>(mp.in_chunk);
+    int rt_it = 0;
+    for (int rt = unit; rt < n_rt; rt += n_units, ++rt_it) {
+      const int m0 = rt * (GEMM_BM * CG) + row_off;
+      float2* dst = s_rn + (rt_it & 1) * GEMM_BM;
+      if (n_chunks == 4) {
+        float2 ta[4][4];
+        stats_fetch<4, 4>(ta, mp.in_stats, mp.M, m0, lane, 0);
+        mbar_wait_parked(&bar_rnempty[rt_it & 1], ((rt_it >> 1) & 1) ^ 1);
+        stats_reduce<4, 4>(ta, dst, lane, 0, cw, mp.C, mp.in_eps);
+      } else {  // 8 chunks (host-checked)
+        float2 ta[4][8];
+        stats_fetch<8, 4>(ta, mp.in_stats, mp.M, m0, lane, 0);
+        mbar_wait_parked(&bar_rnempty[rt_it & 1], ((rt_it >> 1) & 1) ^ 1);
+        stats_reduce<8, 4>(ta, dst, lane, 0, cw, mp.C, mp.in_eps);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_rnfull[rt_it & 1]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int part = (warp - 4) >> 2;
+    const int row_in_tile = q * 32 + lane;
+    uint8_t* slab = sC + (warp - 4) * Cfg::SLAB_BYTES;
+    const uint4 no_res[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    int it = 0, rit = 0, rt_it = 0;
+    auto store_piece = [&](const uint4 (&o)[4], const CUtensorMap* tm, int col, int row0) {
+      // the previous TMA store of this warp must have finished reading the slab before it is refilled
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(slab + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = o[i];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(tm)),
+                     "r"(smem_u32(slab)), "r"(col), "r"(row0)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+    for (int rt = unit; rt < n_rt; rt += n_units, ++rt_it) {
+      const int m0 = rt * (GEMM_BM * CG) + row_off;
+      const int row = m0 + row_in_tile;
+      mbar_wait_parked(&bar_rnfull[rt_it & 1], (rt_it >> 1) & 1);
+      const float2 rn = s_rn[(rt_it & 1) * GEMM_BM + row_in_tile];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_rnempty[rt_it & 1]);
+      // ---- fc1 tiles: hidden = gelu(rstd (acc - mean colsum) + b1') -> scratch rows h0 + ...
+      for (int s = 0; s < NT1; ++s, ++it) {
+        const int as = it & 1;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + part * WCOLS;
+        mbar_wait_parked(&bar_tfull[as], (it >> 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int pc = 0; pc < PIECES; ++pc) {
+          const int col_in_tile = part * WCOLS + pc * 32;
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + pc * 32, acc);
+          tmem_ld_wait();
+          if (pc + 1 == PIECES) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
+          }
+          float v[32];
+          epilogue_values<EPI_BIAS_GELU, true>(acc, s * BN + col_in_tile, p1, rn, no_res, v);
+          uint4 o[4];
+          pack32(v, o);
+          store_piece(o, &tmHs, s * BN + col_in_tile, h0 + q * 32);
+        }
+        // this warp's part of a hidden tile is in L2 once its stores have COMPLETED (not merely been read out of the slab);
+        // bulk groups complete in order, so tile s - 1 is reported after tile s has been issued: the completion latency of the
+        // stores hides behind the next tile instead of stalling this warp before it
+        if (s > 0 && lane == 0) {
+          asm volatile("cp.async.bulk.wait_group %0;" ::"n"(PIECES) : "memory");
+          mbar_arrive(&h_ready[s - 1]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        mbar_arrive(&h_ready[NT1 - 1]);
+      }
+      __syncwarp();
+      // ---- fc2 tiles: out = acc + b2 + x, row statistics of the result for the next block's folded LayerNorm
+      for (int s = 0; s < NT2; ++s, ++it, ++rit) {
+        const int as = it & 1;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + part * WCOLS;
+        mbar_wait_parked(bar_resfull, rit & 1);
+        mbar_wait_parked(&bar_tfull[as], (it >> 1) & 1);
+        tcgen05_fence_after();
+        float2 st_carry = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int pc = 0; pc < PIECES; ++pc) {
+          const int col_in_tile = part * WCOLS + pc * 32;
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + pc * 32, acc);
+          uint4 res_cur[4];
+          const uint8_t* rp = sRes + (col_in_tile >> 5) * (GEMM_BM * 64) + row_in_tile * 64;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) res_cur[i] = *reinterpret_cast<const uint4*>(rp + ((i ^ ((row_in_tile >> 1) & 3)) << 4));
+          if (pc + 1 == PIECES) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_resempty);
+          }
+          tmem_ld_wait();
+          if (pc + 1 == PIECES) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
+          }
+          float v[32];
+          epilogue_values<EPI_BIAS_RESIDUAL, false>(acc, s * BN + col_in_tile, p2, rn, res_cur, v);
+          uint4 o[4];
+          pack32(v, o);
+          if (p2.out_stats != nullptr) {
+            const float2 st_piece = stats32(v);
+            if (pc == 0) {
+              st_carry = st_piece;
+            } else if (row < mp.M) {
+              reinterpret_cast<float2*>(p2.out_stats)[static_cast<size_t>(row) * (mp.C >> 6) + ((s * BN + part * WCOLS) >> 6)] =
+                  stats_merge(st_carry, st_piece, 32.0f);
+            }
+          }
+          store_piece(o, &tmO, s * BN + col_in_tile, m0 + q * 32);
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 }  // namespace lrce
 
 using namespace lrce;
@@ -784,4 +1089,75 @@ extern "C" int lrce_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   if (rc != LRCE_OK) return rc;
   if (pair) return dispatch_epi<256, 2>(tmA, tmB, tmC, p, epilogue, out_fp32, s);
   return wide ? dispatch_epi<256, 1>(tmA, tmB, tmC, p, epilogue, out_fp32, s) : dispatch_epi<128, 1>(tmA, tmB, tmC, p, epilogue, out_fp32, s);
+}
+
+extern "C" size_t lrce_mlp_l2_scratch_bytes(int C) {
+  const int units = sm_count() / 2;
+  return static_cast<size_t>(units > 0 ? units : 1) * 256 * 4 * static_cast<size_t>(C > 0 ? C : 0) * 2;
+}
+
+extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const float* b1, const float* colsum1,
+                                const float* in_stats, int in_chunk, float in_eps, const void* w2, const float* b2, void* out,
+                                int ldo, float* out_stats, void* scratch, size_t scratch_bytes, int M, int C, void* stream) {
+  int rc = require_sm100();
+  if (rc != LRCE_OK) return rc;
+  LRCE_REQUIRE(x && w1 && b1 && colsum1 && in_stats && w2 && b2 && out && scratch, "lrce_mlp_l2_bf16: null operand");
+  LRCE_REQUIRE(M > 0 && (C == 256 || C == 512), "lrce_mlp_l2_bf16: M=%d, C=%d (C must be 256 or 512)", M, C);
+  LRCE_REQUIRE(in_chunk == 64 || (in_chunk == 32 && C == 256), "lrce_mlp_l2_bf16: statistics chunks of %d columns for C=%d", in_chunk, C);
+  LRCE_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                                                 reinterpret_cast<uintptr_t>(scratch)) & 15) == 0,
+               "lrce_mlp_l2_bf16: x / out / scratch must be 16B aligned with row pitches that are multiples of 8");
+  LRCE_REQUIRE(((reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(colsum1) | reinterpret_cast<uintptr_t>(b2) |
+                 reinterpret_cast<uintptr_t>(in_stats)) & 15) == 0 && (out_stats == nullptr || (reinterpret_cast<uintptr_t>(out_stats) & 7) == 0),
+               "lrce_mlp_l2_bf16: bias / column sums / statistics must be 16B aligned");
+  const int sms = sm_count();
+  LRCE_REQUIRE(sms >= 2, "lrce_mlp_l2_bf16: needs CTA pairs");
+  const int n_rt = (M + 255) / 256;
+  int units = sms / 2;
+  if (units > n_rt) units = n_rt;
+  LRCE_REQUIRE(scratch_bytes >= static_cast<size_t>(units) * 256 * 4 * C * 2,
+               "lrce_mlp_l2_bf16: scratch of %zu bytes, %zu needed (lrce_mlp_l2_scratch_bytes)", scratch_bytes,
+               static_cast<size_t>(units) * 256 * 4 * C * 2);
+  const int H = 4 * C;
+  CUtensorMap tmX, tmW1, tmHs, tmHl, tmW2, tmO, tmR;
+  if ((rc = make_tmap_2d_bf16(&tmX, x, C, M, ldx, GEMM_BK, GEMM_BM)) != LRCE_OK) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmW1, w1, C, H, C, GEMM_BK, 128)) != LRCE_OK) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmHs, scratch, H, static_cast<uint64_t>(units) * 256, H, 32, 32, 64)) != LRCE_OK) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmHl, scratch, H, static_cast<uint64_t>(units) * 256, H, GEMM_BK, GEMM_BM)) != LRCE_OK) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmW2, w2, H, C, H, GEMM_BK, 128)) != LRCE_OK) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmO, out, C, M, ldo, 32, 32, 64)) != LRCE_OK) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmR, x, C, M, ldx, 32, GEMM_BM, 64)) != LRCE_OK) return rc;
+  GemmParams p1 = {}, p2 = {};
+  p1.M = M; p1.N = H; p1.K = C; p1.bias = b1; p1.in_stats = in_stats; p1.in_chunk = in_chunk; p1.in_colsum = colsum1; p1.in_eps = in_eps;
+  p2.M = M; p2.N = C; p2.K = H; p2.bias = b2; p2.out = out; p2.ldo = ldo; p2.out_stats = out_stats;
+  MlpL2Params mp;
+  mp.M = M; mp.C = C; mp.in_stats = in_stats; mp.in_chunk = in_chunk; mp.in_eps = in_eps;
+  using Cfg = GemmCfg<256, 2, true>;
+  static thread_local uint64_t configured = 0;
+  if (needs_device_setup(&configured)) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(mlp_l2_kernel, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return LRCE_ECUDA;
+    }
+    mark_device_setup(&configured);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * 2);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1 + pdl_attr(attr + 1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_l2_kernel, tmX, tmW1, tmHs, tmHl, tmW2, tmO, tmR, p1, p2, mp);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(mlp_l2_kernel): %s", cudaGetErrorString(e));
+    return LRCE_ECUDA;
+  }
+  return check_launch("mlp_l2_kernel");
 }

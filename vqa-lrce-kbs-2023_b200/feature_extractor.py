@@ -19,6 +19,8 @@ SWIN_CKPT = "./pretrained_models/swin_base_patch244_window877_kinetics600_22k.pt
 # batch 32 (profiles/README.md): 0,0,0,0 -> 19.8 ms; 12,48,0,0 -> 19.6 ms; 6,24,0,0 -> 20.2 ms; 4,16,0,0 -> 20.9 ms — the HBM
 # traffic saved is paid back in per-launch fill/drain, so whole-batch execution stays the default.
 FUSED_MLP = os.environ.get("LRCE_B200_FUSED_MLP", "1") != "0"  # A/B switch for tools/ (the product default is fused)
+# channel widths whose MLP runs as the row-tile-fused kernel with the hidden rows kept in L2 (A/B switch: LRCE_B200_MLP_L2="")
+MLP_L2_WIDTHS = tuple(int(v) for v in os.environ.get("LRCE_B200_MLP_L2", "256,512").split(",") if v)
 SLAB_SEGMENTS = tuple(int(v) for v in os.environ.get("LRCE_B200_SLABS", "0,0,0,0").split(","))
 
 
@@ -256,6 +258,8 @@ class SwinTransformer3D(_PackedModule):
                     del att
                     if C == 128 and FUSED_MLP:  # stage 1: fc1 -> GELU -> fc2 per 128-row tile, hidden never in HBM
                         ops.mlp_fused(x, b["w1"], b["b1"], b["c1"], st_b, 1e-5, b["w2"], b["b2"], out=x, stats_out=st_a)
+                    elif C in MLP_L2_WIDTHS:  # stages 2 / 3: fc1 -> fc2 per 256-row tile of a CTA pair, hidden rows stay in L2
+                        ops.mlp_l2(x, b["w1"], b["b1"], b["c1"], st_b, 1e-5, b["w2"], b["b2"], out=x, stats_out=st_a)
                     else:
                         hid = ops.gemm(x, b["w1"], b["b1"], epilogue=ops.EPI_BIAS_GELU, ln_in=(st_b, b["c1"], 1e-5))
                         ops.gemm(hid, b["w2"], b["b2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=x, out=x, stats_out=st_a)

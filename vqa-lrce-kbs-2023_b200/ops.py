@@ -118,6 +118,32 @@ def mlp_fused(x, w1, b1, colsum1, stats_in, eps_in, w2, b2, *, out=None, stats_o
     return out
 
 
+_mlp_l2_scratch = {}  # (device, stream, C) -> uint8 scratch of lrce_mlp_l2_scratch_bytes(C), reused by every block launched there
+
+
+def mlp_l2(x, w1, b1, colsum1, stats_in, eps_in, w2, b2, *, out=None, stats_out=None):
+    """out = x + fc2(gelu(fc1(LN(x)))) for C = 256 / 512 rows in one kernel whose hidden rows stay in L2 (lrce_mlp_l2_bf16)"""
+    _req(x, torch.bfloat16, "x"); _req(w1, torch.bfloat16, "w1"); _req(w2, torch.bfloat16, "w2")
+    for t, nme in ((b1, "b1"), (colsum1, "colsum1"), (stats_in, "stats_in"), (b2, "b2"), (stats_out, "stats_out")):
+        _req(t, torch.float32, nme)
+    M, C = x.shape
+    assert x.stride(1) == 1 and w1.is_contiguous() and w2.is_contiguous() and w1.shape == (4 * C, C) and w2.shape == (C, 4 * C)
+    assert stats_in.is_contiguous() and stats_in.numel() >= M * (C // stats_chunk(C)) * 2
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.shape == x.shape and out.stride(1) == 1
+    if stats_out is not None:
+        assert stats_out.is_contiguous() and stats_out.numel() >= M * (C // stats_chunk(C)) * 2
+    key = (x.device.index, _stream(), C)
+    scratch = _mlp_l2_scratch.get(key)
+    if scratch is None:
+        scratch = _mlp_l2_scratch[key] = torch.empty(_lib.lib().lrce_mlp_l2_scratch_bytes(C), device=x.device, dtype=torch.uint8)
+    _call("lrce_mlp_l2_bf16", _ptr(x), x.stride(0), _ptr(w1), _ptr(b1), _ptr(colsum1), _ptr(stats_in), stats_chunk(C), float(eps_in),
+          _ptr(w2), _ptr(b2), _ptr(out), out.stride(0), _ptr(stats_out), _ptr(scratch), scratch.numel(), M, C, _stream(),
+          work=(f"M{M}C{C}", 2.0 * M * C * 4 * C * 2, 2.0 * (2 * M * C + 8 * C * C)))
+    return out
+
+
 def layernorm(x, gamma, beta, eps, *, out=None, out_fp32=False):
     """x bf16 (rows, C) contiguous -> LayerNorm over C."""
     _req(x, torch.bfloat16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")

@@ -18,6 +18,8 @@
 //   LayerNorm is never a separate pass inside a Swin block: residual epilogues emit per-row (mean, M2) partials of
 //   what they write, and the next GEMM folds the normalisation into its epilogue (see GemmParams::in_stats).
 // Both operands are K-major, so no transposes exist anywhere; M and K tails are handled by TMA zero fill.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "lrce_common.cuh"
 
@@ -739,6 +741,7 @@ struct MlpL2Params {
   const float* in_stats;  // float2 [M][C / in_chunk]: (mean, M2) partials of x (the producer of x emitted them)
   int in_chunk;
   float in_eps;
+  int l2_hints;  // 0: none; 1: x / residual loads and out stores evict_first; 2: and the scratch + weights evict_last
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -819,17 +822,20 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0, rit = 0, rt_it = 0;
       uint32_t phase = 0;
-      auto load_kb = [&](const CUtensorMap* ta, int a_row, const CUtensorMap* tb, int b_row, int kb) {
+      // the scratch (and the weights every pair re-reads) must survive in L2 next to the x / out streams of the whole chip
+      // (x itself is re-read by the eight fc1 tiles and once more as the residual: normal priority until that last read)
+      const uint64_t pol_stream = l2_policy(mp.l2_hints >= 1 ? 1 : 0), pol_keep = l2_policy(mp.l2_hints >= 2 ? 2 : 0), pol_normal = l2_policy(0);
+      auto load_kb = [&](const CUtensorMap* ta, int a_row, uint64_t pol_a, const CUtensorMap* tb, int b_row, int kb) {
         mbar_wait_parked(&bar_empty[stage], phase ^ 1);
         if (leader) mbar_expect_tx(&bar_full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
-        tma_load_2d_pair(sA + stage * Cfg::A_BYTES, ta, &bar_full[stage], kb * GEMM_BK, a_row);
-        tma_load_2d_pair(sB + stage * Cfg::B_BYTES, tb, &bar_full[stage], kb * GEMM_BK, b_row);
+        tma_load_2d_pair_hint(sA + stage * Cfg::A_BYTES, ta, &bar_full[stage], kb * GEMM_BK, a_row, pol_a);
+        tma_load_2d_pair_hint(sB + stage * Cfg::B_BYTES, tb, &bar_full[stage], kb * GEMM_BK, b_row, pol_keep);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
       for (int rt = unit; rt < n_rt; rt += n_units, ++rt_it) {
         const int m0 = rt * (GEMM_BM * CG) + row_off;
         for (int s = 0; s < NT1; ++s)
-          for (int kb = 0; kb < nkb1; ++kb) load_kb(&tmX, m0, &tmW1, s * BN + cta_rank * (BN / 2), kb);
+          for (int kb = 0; kb < nkb1; ++kb) load_kb(&tmX, m0, pol_normal, &tmW1, s * BN + cta_rank * (BN / 2), kb);
         for (int s = 0; s < NT2; ++s) {
           for (int kb = 0; kb < nkb2; ++kb) {
             if (s == 0 && (kb & 3) == 0) {
@@ -837,13 +843,14 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               mbar_wait_parked(&h_ready[kb >> 2], rt_it & 1);
               asm volatile("fence.proxy.async;" ::: "memory");
             }
-            load_kb(&tmHl, h0, &tmW2, s * BN + cta_rank * (BN / 2), kb);
+            load_kb(&tmHl, h0, pol_keep, &tmW2, s * BN + cta_rank * (BN / 2), kb);
           }
           // the residual rows of this fc2 tile (= x, not yet overwritten: the tile's own epilogue does that), a main loop ahead
           mbar_wait_parked(bar_resempty, (rit & 1) ^ 1);
           mbar_expect_tx(bar_resfull, Cfg::RES_BYTES);
 #pragma unroll
-          for (int pc = 0; pc < BN / 32; ++pc) tma_load_2d(sRes + pc * (GEMM_BM * 64), &tmR, bar_resfull, s * BN + pc * 32, m0);
+          for (int pc = 0; pc < BN / 32; ++pc)
+            tma_load_2d_hint(sRes + pc * (GEMM_BM * 64), &tmR, bar_resfull, s * BN + pc * 32, m0, pol_stream);
           ++rit;
         }
       }
@@ -910,7 +917,8 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     uint8_t* slab = sC + (warp - 4) * Cfg::SLAB_BYTES;
     const uint4 no_res[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     int it = 0, rit = 0, rt_it = 0;
-    auto store_piece = [&](const uint4 (&o)[4], const CUtensorMap* tm, int col, int row0) {
+    const uint64_t pol_stream = l2_policy(mp.l2_hints >= 1 ? 1 : 0), pol_keep = l2_policy(mp.l2_hints >= 2 ? 2 : 0);
+    auto store_piece = [&](const uint4 (&o)[4], const CUtensorMap* tm, int col, int row0, uint64_t pol) {
       // the previous TMA store of this warp must have finished reading the slab before it is refilled
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
@@ -919,9 +927,9 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
                          reinterpret_cast<uint64_t>(tm)),
-                     "r"(smem_u32(slab)), "r"(col), "r"(row0)
+                     "r"(smem_u32(slab)), "r"(col), "r"(row0), "l"(pol)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -954,7 +962,7 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           epilogue_values<EPI_BIAS_GELU, true>(acc, s * BN + col_in_tile, p1, rn, no_res, v);
           uint4 o[4];
           pack32(v, o);
-          store_piece(o, &tmHs, s * BN + col_in_tile, h0 + q * 32);
+          store_piece(o, &tmHs, s * BN + col_in_tile, h0 + q * 32, pol_keep);
         }
         // this warp's part of a hidden tile is in L2 once its stores have COMPLETED (not merely been read out of the slab);
         // bulk groups complete in order, so tile s - 1 is reported after tile s has been issued: the completion latency of the
@@ -1010,7 +1018,7 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                   stats_merge(st_carry, st_piece, 32.0f);
             }
           }
-          store_piece(o, &tmO, s * BN + col_in_tile, m0 + q * 32);
+          store_piece(o, &tmO, s * BN + col_in_tile, m0 + q * 32, pol_stream);
         }
       }
     }
@@ -1132,6 +1140,11 @@ extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const fl
   p2.M = M; p2.N = C; p2.K = H; p2.bias = b2; p2.out = out; p2.ldo = ldo; p2.out_stats = out_stats;
   MlpL2Params mp;
   mp.M = M; mp.C = C; mp.in_stats = in_stats; mp.in_chunk = in_chunk; mp.in_eps = in_eps;
+  static const int hints = [] {
+    const char* e = getenv("LRCE_B200_MLP_L2_HINTS");  // A/B runs of tools/
+    return e ? atoi(e) : 2;
+  }();
+  mp.l2_hints = hints;
   using Cfg = GemmCfg<256, 2, true>;
   static thread_local uint64_t configured = 0;
   if (needs_device_setup(&configured)) {

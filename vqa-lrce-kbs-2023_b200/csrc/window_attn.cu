@@ -40,6 +40,8 @@
 // tensor core.
 // The S accumulator is released as soon as a warp has its 40 scores in registers, so S(j+1) is computed under the
 // softmax of unit j.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "lrce_common.cuh"
 #include "remap.cuh"
@@ -202,7 +204,7 @@ struct WaItemCtx {
   const bf16* bias_dense;
   bf16* out;
   StageGeom g;
-  int n_items, nwin, T, C, u_lo, n_my;
+  int n_items, nwin, T, C, head0, item0, head_step, n_my;
   float scale_log2e;
   bool shifted;
 };
@@ -309,7 +311,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     }
   };
 
-  int head = cx.u_lo / cx.n_items, item = cx.u_lo - head * cx.n_items;
+  int head = cx.head0, item = cx.item0;
   int seg = item / cx.nwin, win = item - seg * cx.nwin;
   int head_loaded = -1;
   for (int j = 0; j < cx.n_my; ++j) {
@@ -386,7 +388,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
     dst_prev = dst;
     if (++win == cx.nwin) {
       win = 0;
-      if (++seg * cx.nwin == cx.n_items) { seg = 0; ++head; }
+      if (++seg * cx.nwin == cx.n_items) { seg = 0; head += cx.head_step; }
     }
   }
   if (cx.n_my > 0) store_o(cx.n_my - 1);
@@ -395,7 +397,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
 template <bool PROF>
 __global__ void __launch_bounds__(WA_THREADS, 1)
 window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ out, const bf16* __restrict__ bias_dense,
-                        StageGeom g, int n_seg, int C, int n_heads, float scale_log2e, long long* prof) {
+                        StageGeom g, int n_seg, int C, int n_heads, int paired, float scale_log2e, long long* prof) {
   // NOTE: pointers must stay derived from the __shared__ array itself (no integer round trip), otherwise the compiler
   // falls back to generic LD/ST for every shared-memory access
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -418,11 +420,19 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
   const int n_items = n_seg * nwin;
   const bool shifted = (g.sd | g.sh | g.sw) != 0;
   // work units are (head, segment, window) triples in head-major order; every CTA takes one contiguous, equally sized
-  // range, so a CTA changes head (and reloads the 50 KB bias table) at most ceil(heads / CTAs) + 1 times
-  const long long n_units = static_cast<long long>(n_heads) * n_items;
-  const int u_lo = static_cast<int>(n_units * blockIdx.x / gridDim.x);
-  const int u_hi = static_cast<int>(n_units * (blockIdx.x + 1) / gridDim.x);
+  // range, so a CTA changes head (and reloads the 50 KB bias table) at most ceil(heads / CTAs) + 1 times.
+  // paired: two heads share every 128-byte line of a q / k / v row (64 B per head), so CTAs 2k and 2k + 1 walk the SAME
+  // (head pair, segment, window) range, one with the even and one with the odd head of each pair: the second half of every line
+  // is an L2 hit a few hundred nanoseconds after the first instead of a second DRAM read tens of microseconds later (with plain
+  // head-major ranges over 148 CTAs the two heads of a line drift apart and stages 2-4 read their input twice)
+  const int n_groups = paired ? n_heads / 2 : n_heads, head_step = paired ? 2 : 1;
+  const int worker = paired ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = paired ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const long long n_units = static_cast<long long>(n_groups) * n_items;
+  const int u_lo = static_cast<int>(n_units * worker / n_workers);
+  const int u_hi = static_cast<int>(n_units * (worker + 1) / n_workers);
   const int n_my = u_hi - u_lo;
+  const int head0 = (u_lo / n_items) * head_step + (paired ? static_cast<int>(blockIdx.x & 1) : 0), item0 = u_lo % n_items;
   if (PROF && blockIdx.x == 0 && tid == 0) prof[24 * 8 + 2] = clock64();
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled TMA / UMMA tiles assume an aligned window
 
@@ -471,7 +481,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
       // unit -> TMA coordinates: channel of the head's q slice, (x, y) of the parts before / behind the seam (only the
       // part behind the seam can wrap), first frame row of the segment
       struct Coord { int cq, xa, xb, ya, yb, ds; };
-      int head = u_lo / n_items, item = u_lo - head * n_items;
+      int head = head0, item = item0;
       int seg = item / nwin, win = item - seg * nwin;
       auto coord_next = [&]() {
         Coord k;
@@ -480,7 +490,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
         k.cq = head * 32; k.ds = seg * 3;
         if (++win == nwin) {
           win = 0;
-          if (++seg * nwin == n_items) { seg = 0; ++head; }
+          if (++seg * nwin == n_items) { seg = 0; head += head_step; }
         }
         return k;
       };
@@ -585,7 +595,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
     // ===================================================================== softmax + epilogue (20 warps)
     WaItemCtx cx;
     cx.bias_dense = bias_dense; cx.out = out; cx.g = g; cx.n_items = n_items; cx.nwin = nwin; cx.T = T; cx.C = C;
-    cx.u_lo = u_lo; cx.n_my = n_my; cx.scale_log2e = scale_log2e; cx.shifted = shifted;
+    cx.head0 = head0; cx.item0 = item0; cx.head_step = head_step; cx.n_my = n_my; cx.scale_log2e = scale_log2e; cx.shifted = shifted;
     if (warp < 16) softmax_warp<0, PROF>(sh, tmem_base, warp & 3, warp >> 2, cx);
     else softmax_warp<1, PROF>(sh, tmem_base, warp & 3, warp & 3, cx);
   }
@@ -711,16 +721,24 @@ static int window_attention_launch(const void* qkv, void* out, const void* bias_
   if (rc != LRCE_OK) return rc;
   const long long n_units = static_cast<long long>(n_seg) * windows_per_segment(g) * n_heads;
   int grid = sm_count();  // one persistent CTA per SM (it owns all 512 TMEM columns)
-  if (grid > n_units) grid = static_cast<int>(n_units);
+  // pairs of CTAs walk the two heads of a 128-byte q / k / v line together (see the kernel); LRCE_B200_ATTN_ALIGN=0: plain
+  // head-major ranges (A/B runs of tools/)
+  static const bool align_heads = [] {
+    const char* e = getenv("LRCE_B200_ATTN_ALIGN");
+    return !(e && e[0] == '0');
+  }();
+  const int paired = (align_heads && n_heads % 2 == 0 && grid >= 2) ? 1 : 0;
+  if (paired) grid &= ~1;
+  if (grid > n_units) grid = static_cast<int>(paired ? (n_units & ~1LL) : n_units);
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (prof != nullptr)  // instrumented instantiation
     e = launch_pdl(window_attention_kernel<true>, dim3(grid), dim3(WA_THREADS), WA_SMEM, s, *maps, reinterpret_cast<bf16*>(out),
-                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e, prof);
+                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, paired, scale_log2e, prof);
   else
     e = launch_pdl(window_attention_kernel<false>, dim3(grid), dim3(WA_THREADS), WA_SMEM, s, *maps, reinterpret_cast<bf16*>(out),
-                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, scale_log2e, static_cast<long long*>(nullptr));
+                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, paired, scale_log2e, static_cast<long long*>(nullptr));
   if (e != cudaSuccess) {
     set_error("cudaLaunchKernelEx(window_attention_kernel): %s", cudaGetErrorString(e));
     return LRCE_ECUDA;

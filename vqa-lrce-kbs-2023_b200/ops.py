@@ -137,6 +137,8 @@ def mlp_l2(x, w1, b1, colsum1, stats_in, eps_in, w2, b2, *, out=None, stats_out=
     key = (x.device.index, _stream(), C)
     scratch = _mlp_l2_scratch.get(key)
     if scratch is None:
+        if len(_mlp_l2_scratch) >= 8:  # (device, stream, width) combinations are few; drop the oldest rather than grow
+            _mlp_l2_scratch.pop(next(iter(_mlp_l2_scratch)))
         scratch = _mlp_l2_scratch[key] = torch.empty(_lib.lib().lrce_mlp_l2_scratch_bytes(C), device=x.device, dtype=torch.uint8)
     _call("lrce_mlp_l2_bf16", _ptr(x), x.stride(0), _ptr(w1), _ptr(b1), _ptr(colsum1), _ptr(stats_in), stats_chunk(C), float(eps_in),
           _ptr(w2), _ptr(b2), _ptr(out), out.stride(0), _ptr(stats_out), _ptr(scratch), scratch.numel(), M, C, _stream(),

@@ -140,9 +140,10 @@ int lrce_mlp_fused_bf16(const void* x, int ldx, const void* w1, const float* b1,
                         float in_eps, const void* w2, const float* b2, void* out, int ldo, float* out_stats, int M, int C,
                         void* stream);
 
-/* The Swin MLP block of the stage-2 / stage-3 blocks (C = 256 / 512) as ONE kernel with the hidden activations kept in L2
+/* The Swin MLP block of the stage-2 / stage-3 blocks (C = 256 / 512; C = 128 is accepted with in_chunk = 32, but
+ * lrce_mlp_fused_bf16 is the faster kernel there) as ONE kernel with the hidden activations kept in L2
  * (csrc/gemm_tc.cu, mlp_l2_kernel): same contract as lrce_mlp_fused_bf16 (video_swin_ori.py:40-57, :284-285, :304), statistics
- * in chunks of `in_chunk` = 64 columns. Every CTA pair walks its 256-row tiles through fc1 (folded LayerNorm + bias + GELU) into
+ * in chunks of `in_chunk` = 64 columns (32 for C = 128). Every CTA pair walks its 256-row tiles through fc1 (folded LayerNorm + bias + GELU) into
  * its private 256 x 4C bf16 slice of `scratch`, then through fc2 (K = 4C, bias + residual x + out_stats) reading that slice
  * back; the scratch (lrce_mlp_l2_scratch_bytes(C) bytes, 16-byte aligned, contents undefined afterwards) is overwritten by
  * every row tile and therefore stays in L2. Replaces two lrce_gemm_bf16 calls (EPI_BIAS_GELU + EPI_BIAS_RESIDUAL) and the

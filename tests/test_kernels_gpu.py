@@ -157,7 +157,7 @@ def test_mlp_fused_vs_two_gemms_and_torch(ops, M, inplace):
     assert ((got[..., 1] - want[..., 1]).abs() / want[..., 1].clamp_min(1e-3)).max().item() < 2e-2
 
 
-@pytest.mark.parametrize("C", [256, 512])
+@pytest.mark.parametrize("C", [128, 256, 512])
 @pytest.mark.parametrize("M", [256, 300, 148 * 128 * 2 + 77])
 @pytest.mark.parametrize("inplace", [False, True])
 def test_mlp_l2_is_the_two_gemm_path(ops, C, M, inplace):

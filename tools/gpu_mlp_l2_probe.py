@@ -50,7 +50,7 @@ def run(name, fn, flop):
     return ms
 
 
-for M, C in ((56448, 512), (225792, 256)):
+for M, C in ((56448, 512), (225792, 256), (903168, 128)):
     x = (torch.randn(M, C, device=dev) * 0.8).bfloat16()
     w1 = (torch.randn(4 * C, C, device=dev) * 0.04).bfloat16()
     w2 = (torch.randn(C, 4 * C, device=dev) * 0.04).bfloat16()
@@ -69,6 +69,11 @@ for M, C in ((56448, 512), (225792, 256)):
         ops.mlp_l2(x, w1, b1, c1, st_in, 1e-5, w2, b2, out=out, stats_out=st_out)
 
     print(f"M={M} C={C}", flush=True)
+    def sm_fused():
+        ops.mlp_fused(x, w1, b1, c1, st_in, 1e-5, w2, b2, out=out, stats_out=st_out)
+
     for rep in range(2):
         run("two GEMM launches", two, flop)
+        if C == 128:
+            run("mlp_fused (in-SM)", sm_fused, flop)
         run("mlp_l2 (one launch)", fused, flop)

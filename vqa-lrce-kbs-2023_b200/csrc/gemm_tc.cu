@@ -744,12 +744,14 @@ struct MlpL2Params {
   int l2_hints;  // 0: none; 1: x / residual loads and out stores evict_first; 2: and the scratch + weights evict_last
 };
 
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmHs, const __grid_constant__ CUtensorMap tmHl,
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO,
               const __grid_constant__ CUtensorMap tmR, const GemmParams p1, const GemmParams p2, const MlpL2Params mp) {
-  constexpr int BN = 256, CG = 2;
+  constexpr int CG = 2;
+  constexpr int KB_PER_TILE = BN / GEMM_BK;  // k-blocks of fc2 per hidden tile of fc1
   using Cfg = GemmCfg<BN, CG, true>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int WCOLS = BN / 4, PIECES = WCOLS / 32;
@@ -838,9 +840,9 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           for (int kb = 0; kb < nkb1; ++kb) load_kb(&tmX, m0, pol_normal, &tmW1, s * BN + cta_rank * (BN / 2), kb);
         for (int s = 0; s < NT2; ++s) {
           for (int kb = 0; kb < nkb2; ++kb) {
-            if (s == 0 && (kb & 3) == 0) {
-              // hidden columns [64 kb, 64 kb + 256) = fc1 tile kb / 4 of this row tile: stored and complete?
-              mbar_wait_parked(&h_ready[kb >> 2], rt_it & 1);
+            if (s == 0 && kb % KB_PER_TILE == 0) {
+              // hidden columns [64 kb, 64 kb + BN) = fc1 tile kb / KB_PER_TILE of this row tile: stored and complete?
+              mbar_wait_parked(&h_ready[kb / KB_PER_TILE], rt_it & 1);
               asm volatile("fence.proxy.async;" ::: "memory");
             }
             load_kb(&tmHl, h0, pol_keep, &tmW2, s * BN + cta_rank * (BN / 2), kb);
@@ -1011,9 +1013,12 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           pack32(v, o);
           if (p2.out_stats != nullptr) {
             const float2 st_piece = stats32(v);
-            if (pc == 0) {
+            if (PIECES == 1) {  // 128-wide tiles: 32-column chunks
+              if (row < mp.M)
+                reinterpret_cast<float2*>(p2.out_stats)[static_cast<size_t>(row) * (mp.C >> 5) + ((s * BN + col_in_tile) >> 5)] = st_piece;
+            } else if (pc == 0) {
               st_carry = st_piece;
-            } else if (row < mp.M) {
+            } else if (row < mp.M) {  // 256-wide tiles: this warp's two pieces form one 64-column chunk
               reinterpret_cast<float2*>(p2.out_stats)[static_cast<size_t>(row) * (mp.C >> 6) + ((s * BN + part * WCOLS) >> 6)] =
                   stats_merge(st_carry, st_piece, 32.0f);
             }
@@ -1110,8 +1115,8 @@ extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const fl
   int rc = require_sm100();
   if (rc != LRCE_OK) return rc;
   LRCE_REQUIRE(x && w1 && b1 && colsum1 && in_stats && w2 && b2 && out && scratch, "lrce_mlp_l2_bf16: null operand");
-  LRCE_REQUIRE(M > 0 && (C == 256 || C == 512), "lrce_mlp_l2_bf16: M=%d, C=%d (C must be 256 or 512)", M, C);
-  LRCE_REQUIRE(in_chunk == 64 || (in_chunk == 32 && C == 256), "lrce_mlp_l2_bf16: statistics chunks of %d columns for C=%d", in_chunk, C);
+  LRCE_REQUIRE(M > 0 && (C == 128 || C == 256 || C == 512), "lrce_mlp_l2_bf16: M=%d, C=%d (C must be 128, 256 or 512)", M, C);
+  LRCE_REQUIRE(in_chunk == (C == 128 ? 32 : 64), "lrce_mlp_l2_bf16: statistics chunks of %d columns for C=%d", in_chunk, C);
   LRCE_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
                                                  reinterpret_cast<uintptr_t>(scratch)) & 15) == 0,
                "lrce_mlp_l2_bf16: x / out / scratch must be 16B aligned with row pitches that are multiples of 8");
@@ -1129,10 +1134,11 @@ extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const fl
   const int H = 4 * C;
   CUtensorMap tmX, tmW1, tmHs, tmHl, tmW2, tmO, tmR;
   if ((rc = make_tmap_2d_bf16(&tmX, x, C, M, ldx, GEMM_BK, GEMM_BM)) != LRCE_OK) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmW1, w1, C, H, C, GEMM_BK, 128)) != LRCE_OK) return rc;
+  const int BN = C == 128 ? 128 : 256;  // tile width of both products (fc2 has N = C columns)
+  if ((rc = make_tmap_2d_bf16(&tmW1, w1, C, H, C, GEMM_BK, BN / 2)) != LRCE_OK) return rc;
   if ((rc = make_tmap_2d_bf16(&tmHs, scratch, H, static_cast<uint64_t>(units) * 256, H, 32, 32, 64)) != LRCE_OK) return rc;
   if ((rc = make_tmap_2d_bf16(&tmHl, scratch, H, static_cast<uint64_t>(units) * 256, H, GEMM_BK, GEMM_BM)) != LRCE_OK) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmW2, w2, H, C, H, GEMM_BK, 128)) != LRCE_OK) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmW2, w2, H, C, H, GEMM_BK, BN / 2)) != LRCE_OK) return rc;
   if ((rc = make_tmap_2d_bf16(&tmO, out, C, M, ldo, 32, 32, 64)) != LRCE_OK) return rc;
   if ((rc = make_tmap_2d_bf16(&tmR, x, C, M, ldx, 32, GEMM_BM, 64)) != LRCE_OK) return rc;
   GemmParams p1 = {}, p2 = {};
@@ -1145,12 +1151,15 @@ extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const fl
     return e ? atoi(e) : 2;
   }();
   mp.l2_hints = hints;
-  using Cfg = GemmCfg<256, 2, true>;
+  auto kern = BN == 128 ? mlp_l2_kernel<128> : mlp_l2_kernel<256>;
+  const int smem_bytes = BN == 128 ? GemmCfg<128, 2, true>::SMEM_BYTES : GemmCfg<256, 2, true>::SMEM_BYTES;
   static thread_local uint64_t configured = 0;
   if (needs_device_setup(&configured)) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_l2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 2, true>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp_l2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, 2, true>::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(mlp_l2_kernel, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(mlp_l2_kernel): %s", cudaGetErrorString(e));
       return LRCE_ECUDA;
     }
     mark_device_setup(&configured);
@@ -1158,7 +1167,7 @@ extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const fl
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * 2);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1167,7 +1176,7 @@ extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const fl
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1 + pdl_attr(attr + 1);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_l2_kernel, tmX, tmW1, tmHs, tmHl, tmW2, tmO, tmR, p1, p2, mp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmX, tmW1, tmHs, tmHl, tmW2, tmO, tmR, p1, p2, mp);
   if (e != cudaSuccess) {
     set_error("cudaLaunchKernelEx(mlp_l2_kernel): %s", cudaGetErrorString(e));
     return LRCE_ECUDA;

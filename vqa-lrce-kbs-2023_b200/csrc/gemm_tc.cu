@@ -741,7 +741,9 @@ struct MlpL2Params {
   const float* in_stats;  // float2 [M][C / in_chunk]: (mean, M2) partials of x (the producer of x emitted them)
   int in_chunk;
   float in_eps;
-  int l2_hints;  // 0: none; 1: x / residual loads and out stores evict_first; 2: and the scratch + weights evict_last
+  int l2_hints;  // 0: none; 1: x / residual loads and out stores evict_first; 2: and the scratch + weights evict_last;
+                 // 3: and the hidden rows demoted by their last reader; 4: and discarded (no write-back) once that read has landed
+  uint8_t* scratch;
 };
 
 template <int BN>
@@ -845,7 +847,9 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               mbar_wait_parked(&h_ready[kb / KB_PER_TILE], rt_it & 1);
               asm volatile("fence.proxy.async;" ::: "memory");
             }
-            load_kb(&tmHl, h0, pol_keep, &tmW2, s * BN + cta_rank * (BN / 2), kb);
+            // the last fc2 tile is the last reader of the hidden rows: demote them, so that what the L2 evicts next are these dead
+            // lines (rewritten by the next row tile anyway) rather than hidden rows that are still waiting to be read
+            load_kb(&tmHl, h0, (mp.l2_hints >= 3 && s + 1 == NT2) ? pol_stream : pol_keep, &tmW2, s * BN + cta_rank * (BN / 2), kb);
           }
           // the residual rows of this fc2 tile (= x, not yet overwritten: the tile's own epilogue does that), a main loop ahead
           mbar_wait_parked(bar_resempty, (rit & 1) ^ 1);
@@ -864,6 +868,7 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
       int stage = 0, it = 0;
       uint32_t phase = 0;
+      uint8_t* h_pair = mp.scratch + static_cast<size_t>(unit) * (GEMM_BM * CG) * (8 * mp.C);  // the pair's 256 scratch rows (4C bf16 each)
       for (int rt = unit; rt < n_rt; rt += n_units) {
         for (int s = 0; s < NT1 + NT2; ++s, ++it) {
           const int n_kb = s < NT1 ? nkb1 : nkb2;
@@ -882,6 +887,13 @@ mlp_l2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               umma_commit_pair(&bar_empty[stage]);
             }
             __syncwarp();
+            if (mp.l2_hints >= 4 && s + 1 == NT1 + NT2) {
+              // the last fc2 tile's copy of hidden columns [64 kb, 64 kb + 64) has landed in both CTAs: those 256 x 128 B of the
+              // scratch are dead until the next row tile rewrites them -> let the L2 drop them without a write-back
+#pragma unroll
+              for (int r = 0; r < (GEMM_BM * CG) / 32; ++r)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(h_pair + static_cast<size_t>(r * 32 + lane) * (8 * mp.C) + kb * 128) : "memory");
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (elect_one()) umma_commit_pair(&bar_tfull[as]);
@@ -1148,9 +1160,10 @@ extern "C" int lrce_mlp_l2_bf16(const void* x, int ldx, const void* w1, const fl
   mp.M = M; mp.C = C; mp.in_stats = in_stats; mp.in_chunk = in_chunk; mp.in_eps = in_eps;
   static const int hints = [] {
     const char* e = getenv("LRCE_B200_MLP_L2_HINTS");  // A/B runs of tools/
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 4;
   }();
   mp.l2_hints = hints;
+  mp.scratch = static_cast<uint8_t*>(scratch);
   auto kern = BN == 128 ? mlp_l2_kernel<128> : mlp_l2_kernel<256>;
   const int smem_bytes = BN == 128 ? GemmCfg<128, 2, true>::SMEM_BYTES : GemmCfg<256, 2, true>::SMEM_BYTES;
   static thread_local uint64_t configured = 0;

@@ -126,12 +126,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw64_lbo(uint32_t smem_addr, uint3
   return d;
 }
 
+// q / k / v slices are read once (by this CTA and, at the same moment, by its partner on the other head of the line) and are dead
+// afterwards: `policy` = L2 evict_first keeps them from displacing the attention output the projection GEMM reads next
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
+                                            int c3, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "%7;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* v) {
@@ -397,7 +399,7 @@ __device__ __forceinline__ void softmax_warp(const WaShared& sh, uint32_t tmem_b
 template <bool PROF>
 __global__ void __launch_bounds__(WA_THREADS, 1)
 window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ out, const bf16* __restrict__ bias_dense,
-                        StageGeom g, int n_seg, int C, int n_heads, int paired, float scale_log2e, long long* prof) {
+                        StageGeom g, int n_seg, int C, int n_heads, int paired, int in_evict_first, float scale_log2e, long long* prof) {
   // NOTE: pointers must stay derived from the __shared__ array itself (no integer round trip), otherwise the compiler
   // falls back to generic LD/ST for every shared-memory access
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -478,6 +480,7 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
       const int lw = 31 - __clz(g.W / 7);  // H/7 and W/7 are powers of two on this path (8, 4, 2, 1)
       const int nh_mask = g.H / 7 - 1, nw_mask = g.W / 7 - 1;
       const uint32_t smem0 = smem_u32(smem);
+      const uint64_t pol_in = l2_policy(in_evict_first ? 1 : 0);
       // unit -> TMA coordinates: channel of the head's q slice, (x, y) of the parts before / behind the seam (only the
       // part behind the seam can wrap), first frame row of the segment
       struct Coord { int cq, xa, xb, ya, yb, ds; };
@@ -500,15 +503,15 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
         uint64_t* bar = &sh.qk_full[buf];
         timed_wait<PROF>(sh, &sh.qk_empty[buf], ((j >> 1) & 1) ^ 1, 0, j);
         mbar_expect_tx(bar, WA_QK_TX_BYTES);
-        tma_load_4d(sk + 0 * 64, &maps.m[0], bar, C + k.cq, k.xa, k.ya, k.ds);
-        tma_load_4d(sk + 48 * 64, &maps.m[1], bar, C + k.cq, k.xb, k.ya, k.ds);
-        tma_load_4d(sk + 88 * 64, &maps.m[2], bar, C + k.cq, k.xa, k.yb, k.ds);
-        tma_load_4d(sk + 128 * 64, &maps.m[3], bar, C + k.cq, k.xb, k.yb, k.ds);
-        tma_load_4d(sq + 0 * 64, &maps.m[0], bar, k.cq, k.xa, k.ya, k.ds);
-        tma_load_4d(sq + 48 * 64, &maps.m[1], bar, k.cq, k.xb, k.ya, k.ds);
-        tma_load_4d(sq + 88 * 64, &maps.m[2], bar, k.cq, k.xa, k.yb, k.ds);
+        tma_load_4d(sk + 0 * 64, &maps.m[0], bar, C + k.cq, k.xa, k.ya, k.ds, pol_in);
+        tma_load_4d(sk + 48 * 64, &maps.m[1], bar, C + k.cq, k.xb, k.ya, k.ds, pol_in);
+        tma_load_4d(sk + 88 * 64, &maps.m[2], bar, C + k.cq, k.xa, k.yb, k.ds, pol_in);
+        tma_load_4d(sk + 128 * 64, &maps.m[3], bar, C + k.cq, k.xb, k.yb, k.ds, pol_in);
+        tma_load_4d(sq + 0 * 64, &maps.m[0], bar, k.cq, k.xa, k.ya, k.ds, pol_in);
+        tma_load_4d(sq + 48 * 64, &maps.m[1], bar, k.cq, k.xb, k.ya, k.ds, pol_in);
+        tma_load_4d(sq + 88 * 64, &maps.m[2], bar, k.cq, k.xa, k.yb, k.ds, pol_in);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) tma_load_4d(sq + (128 + 32 * r) * 64, &maps.m[3], bar, k.cq, k.xb, k.yb, k.ds);
+        for (int r = 0; r < 4; ++r) tma_load_4d(sq + (128 + 32 * r) * 64, &maps.m[3], bar, k.cq, k.xb, k.yb, k.ds, pol_in);
       };
       // q / k of unit j+1 are requested BEFORE v of unit j: their buffer is free as soon as S(j-1) has been issued, a whole
       // unit earlier than the v buffer (P v(j-2))
@@ -525,10 +528,10 @@ window_attention_kernel(const __grid_constant__ WaMaps maps, bf16* __restrict__ 
         uint64_t* bar = &sh.v_full[buf];
         timed_wait<PROF>(sh, &sh.v_empty[buf], ((j >> 1) & 1) ^ 1, 3, j);
         mbar_expect_tx(bar, WA_V_TX_BYTES);
-        tma_load_4d(sv + 0 * 64, &maps.m[0], bar, 2 * C + cur.cq, cur.xa, cur.ya, cur.ds);
-        tma_load_4d(sv + 48 * 64, &maps.m[1], bar, 2 * C + cur.cq, cur.xb, cur.ya, cur.ds);
-        tma_load_4d(sv + 88 * 64, &maps.m[2], bar, 2 * C + cur.cq, cur.xa, cur.yb, cur.ds);
-        tma_load_4d(sv + 128 * 64, &maps.m[3], bar, 2 * C + cur.cq, cur.xb, cur.yb, cur.ds);
+        tma_load_4d(sv + 0 * 64, &maps.m[0], bar, 2 * C + cur.cq, cur.xa, cur.ya, cur.ds, pol_in);
+        tma_load_4d(sv + 48 * 64, &maps.m[1], bar, 2 * C + cur.cq, cur.xb, cur.ya, cur.ds, pol_in);
+        tma_load_4d(sv + 88 * 64, &maps.m[2], bar, 2 * C + cur.cq, cur.xa, cur.yb, cur.ds, pol_in);
+        tma_load_4d(sv + 128 * 64, &maps.m[3], bar, 2 * C + cur.cq, cur.xb, cur.yb, cur.ds, pol_in);
         cur = nxt;
       }
     }
@@ -728,6 +731,10 @@ static int window_attention_launch(const void* qkv, void* out, const void* bias_
     return !(e && e[0] == '0');
   }();
   const int paired = (align_heads && n_heads % 2 == 0 && grid >= 2) ? 1 : 0;
+  static const int in_hint = [] {
+    const char* e = getenv("LRCE_B200_ATTN_IN_HINT");  // A/B runs of tools/
+    return e ? atoi(e) : 1;
+  }();
   if (paired) grid &= ~1;
   if (grid > n_units) grid = static_cast<int>(paired ? (n_units & ~1LL) : n_units);
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
@@ -735,10 +742,10 @@ static int window_attention_launch(const void* qkv, void* out, const void* bias_
   cudaError_t e;
   if (prof != nullptr)  // instrumented instantiation
     e = launch_pdl(window_attention_kernel<true>, dim3(grid), dim3(WA_THREADS), WA_SMEM, s, *maps, reinterpret_cast<bf16*>(out),
-                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, paired, scale_log2e, prof);
+                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, paired, in_hint, scale_log2e, prof);
   else
     e = launch_pdl(window_attention_kernel<false>, dim3(grid), dim3(WA_THREADS), WA_SMEM, s, *maps, reinterpret_cast<bf16*>(out),
-                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, paired, scale_log2e, static_cast<long long*>(nullptr));
+                   reinterpret_cast<const bf16*>(bias_dense), g, n_seg, C, n_heads, paired, in_hint, scale_log2e, static_cast<long long*>(nullptr));
   if (e != cudaSuccess) {
     set_error("cudaLaunchKernelEx(window_attention_kernel): %s", cudaGetErrorString(e));
     return LRCE_ECUDA;

@@ -43,9 +43,9 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 
 # gemm_tc_kernel + mlp_l2_kernel launches of Swin + encoder in one batch-32 forward (ncu launch list; BERT's 48 gemm_tc_kernel
 # launches excluded: 304 MB). mlp_l2_kernel is the same pipeline walking fc1 -> fc2 per row tile (20 launches replace 40).
-GEMM_DRAM_BYTES_PER_STEP = (7032.6e6 - 303.7e6) + 5778.1e6 + 3828.7e6 + 4389.7e6
+GEMM_DRAM_BYTES_PER_STEP = (7037.9e6 - 303.7e6) + 5748.7e6 + 3247.5e6 + 3131.5e6
 GEMM_LAUNCHES_NCU = 79.0
-GEMM_TRAFFIC_SOURCE = "profiles/r02_launches_v3_summary.md"
+GEMM_TRAFFIC_SOURCE = "profiles/r02_launches_v4_summary.md"
 
 
 def load_peaks():

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblrce_b200.so")
+# LRCE_B200_LIB: another build of the same library (timing variants of tools/build_variants.sh); it must exist, there is no fallback
+LIB_PATH = os.environ.get("LRCE_B200_LIB") or os.path.join(_HERE, "liblrce_b200.so")
 
 _c = ctypes
 _vp, _i, _f, _ll, _u64, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong, _c.c_ulonglong, _c.c_size_t

@@ -185,7 +185,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 template <bool PROF>
 __device__ __forceinline__ void timed_wait(const WaShared& sh, uint64_t* bar, uint32_t parity, int slot, int item = -1) {
   if (!PROF) {
-    mbar_wait_parked(bar, parity);
+    // Non-blocking test_wait in a tight loop, not the parked try_wait of the other kernels: every wait of this kernel sits on the
+    // per-unit dependency chain (S ready -> softmax -> P ready -> P v -> O ready), and the wake-up of a parked warp costs more
+    // than the issue slots the spinning warps take (forward, same box: 15.40 -> 15.20 ms; the walk kernel is the opposite case:
+    // 818 -> 850 us with spinning waits, its eight compute warps need the slots)
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(done)
+                   : "r"(smem_u32(bar)), "r"(parity)
+                   : "memory");
     return;
   }
   volatile int* abort_flag = reinterpret_cast<volatile int*>(sh.smem + WA_OFF_BAR + 184);

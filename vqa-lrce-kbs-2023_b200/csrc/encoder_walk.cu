@@ -255,7 +255,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       RingPos rp = {0, 0};
       auto acquire = [&]() {
         const uint32_t s = rp.s;
-        mbar_wait_parked(&empty[s], rp.ph ^ 1);
+        mbar_wait_short(&empty[s], rp.ph ^ 1);
         ring_adv(rp, 1, ns);
         return s;
       };
@@ -329,7 +329,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       const uint32_t s = rp.s;
       if (mine) {
         const long long t0 = PROF ? clock64() : 0;
-        mbar_wait_parked(&full[s], rp.ph);
+        mbar_wait_short(&full[s], rp.ph);
         if (PROF) mwait[mph] += clock64() - t0;
         tcgen05_fence_after();
       }
@@ -338,7 +338,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     };
     auto wait_b = [&]() {
       const long long t0 = PROF ? clock64() : 0;
-      mbar_wait_parked(b_ready, br & 1);
+      mbar_wait_short(b_ready, br & 1);
       if (PROF) mwait[3] += clock64() - t0;
       ++br;
       tcgen05_fence_after();
@@ -378,7 +378,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         wait_b();
         lin48(WK_TM_Q);
         ring_adv(rp, 2 * nu, ns);  // K / V slots are consumed by the compute warps
-        mbar_wait_parked(ctx_bar, kstep & 1);  // every unit's ctx slice has landed in xb
+        mbar_wait_short(ctx_bar, kstep & 1);  // every unit's ctx slice has landed in xb
         tcgen05_fence_after();
         lin48(WK_TM_O);
         wait_b();
@@ -468,7 +468,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     };
 
     auto wait_acc = [&]() {
-      mbar_wait_parked(acc_full, af & 1);
+      mbar_wait_short(acc_full, af & 1);
       ++af;
       tcgen05_fence_after();
     };
@@ -487,7 +487,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         bulk_s2c(mapa_u32(smem_u32(G + (buf * WK_CL + rank) * rpc * WK_F), lane), smem_u32(src) + lane * src_stride_bytes, xbytes,
                  mapa_u32(smem_u32(&gbar[buf]), lane));
       }
-      mbar_wait_parked(&gbar[buf], (e >> 1) & 1);
+      mbar_wait_short(&gbar[buf], (e >> 1) & 1);
       ++e;
       return buf;
     };
@@ -612,7 +612,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       signal_b();
       for (int s = 0; s < S; ++s) {
         for (int n = 0; n < L; ++n, ++k) {
-          mbar_wait_parked(&par_bar[k & 1], (k >> 1) & 1);
+          mbar_wait_short(&par_bar[k & 1], (k >> 1) & 1);
           const float* par = par_base + (k & 1) * WK_PB;
           stamp(0);
           // ---- P1: y1 = x + W_sa x + b_sa ; h1 = LN1(y1)
@@ -654,7 +654,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
               qa[0] = a0.x; qa[1] = a0.y; qa[2] = a0.z; qa[3] = a0.w; qa[4] = a1.x; qa[5] = a1.y; qa[6] = a1.z; qa[7] = a1.w;
               qb[0] = b0.x; qb[1] = b0.y; qb[2] = b0.z; qb[3] = b0.w; qb[4] = b1.x; qb[5] = b1.y; qb[6] = b1.z; qb[7] = b1.w;
             }
-            mbar_wait_parked(&full[sk], rk.ph);
+            mbar_wait_short(&full[sk], rk.ph);
             stamp(6);
             const int k_lo = warp * 24;
             uint4 ka[3], kb4[3];
@@ -708,7 +708,7 @@ encoder_walk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             stamp(7);
             // ---- partial P V over the same 24 keys, two output dims per lane: a V row is one conflict-free 128-byte read per
             // warp, the probabilities are shared-memory broadcasts, nothing is shuffled
-            mbar_wait_parked(&full[sv], rv.ph);
+            mbar_wait_short(&full[sv], rv.ph);
             stamp(8);
             float2 o2 = make_float2(0.f, 0.f);
 #pragma unroll

@@ -55,6 +55,23 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
       : "memory");
 }
 
+// the same without a suspend-time hint: the hardware still blocks the thread inside try_wait, but for its own (short) time limit;
+// the walk kernel's chain of ~30 hand-overs per layer-step runs 1.6 % faster with it (805 vs 818 us), a pure test_wait spin 4 %
+// slower (its eight compute warps need the issue slots)
+__device__ __forceinline__ void mbar_wait_short(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT_S:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE_S;\n"
+      "bra LAB_WAIT_S;\n"
+      "DONE_S:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // programmatic dependent launch (host side: launch_pdl / pdl_attr in host_common.h). griddep_wait(): block until the kernels this
 // launch depends on have completed and their writes are visible — before the FIRST global-memory access of the kernel; a no-op
 // for a normal launch. griddep_launch(): this block no longer holds back the start of the next kernel of the stream.
